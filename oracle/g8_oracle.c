@@ -1,0 +1,396 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- CPU restatement (plain C) of the reference's Ozaki-II hot path.
+ * Nothing under gemmul8_b200/ may link, load or call this file; only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs use it, and only as the checker.
+ *
+ * What it restates (all paths relative to /root/reference/GEMMul8/src/):
+ *   g8o_amax_*            find_max.hpp:26-64            row / column |max| of op(A), op(B)
+ *   g8o_upper_bound_i8    scaling.hpp:3-46              ceil(|a| * 2^s) -> int8 (accurate-mode bound matrices)
+ *   g8o_accu_shift        scaling_accu_real.hpp:6-18    floor(log2P - 0.5000001*log2(max)) -- see NOTE below
+ *   g8o_fast_shift        scaling_fast_real.hpp:6-22    Cauchy-Schwarz shift from round-up sum of squares
+ *   g8o_split_*           scaling.hpp:99-235 + mod.hpp:8-93,194-284  trunc(a*2^s) mod p_i -> int8 planes
+ *   g8o_gemm_mod_i8       gemmul8_real.hpp:144-191 + conv_hi2mid_real.hpp:9-25  exact int GEMM then symmetric mod
+ *   g8o_crt_*             inverse_scaling_real.hpp:8-89,171-186  FMA chain, rint, unscale, alpha/beta epilogue
+ *   complex variants      gemmul8_complex.hpp:150-200, conv_hi2mid_complex.hpp:46-127, inverse_scaling_complex.hpp
+ *
+ * The arithmetic is done with exact wide integers (unsigned __int128) instead of the reference's
+ * int32 / int64 / fp special cases: all three of its representations denote the same integer
+ * trunc(a*2^s), so the residues are identical by construction.
+ *
+ * NOTE (parity pin): the device computes shifts with __log2f (MUFU.LG2, not reproducible on a CPU).
+ * g8o_accu_shift / g8o_fast_shift therefore also report an `ambiguous` flag when the floor() argument
+ * is within 2^-12 of an integer; tests accept either neighbour there and then feed the DEVICE shifts
+ * back into the split/GEMM/CRT restatement, which must match bit for bit.  The restatement is pinned by
+ * the reference's only known-answer vector (sample/dgemm_cuBLASLt_int8.cu:26-40, tests/golden/) and, on
+ * the GPU box, by the unmodified reference library (oracle/_ref).
+ *
+ * Build: gcc -O2 -fPIC -shared -ffp-contract=off g8_oracle.c -lm   (see oracle/Makefile)
+ */
+#include <fenv.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef unsigned __int128 u128;
+
+/* ---------------------------------------------------------------- helpers */
+
+/* symmetric residue as `wrapping` (mod.hpp:8-12): r in [-floor(p/2), floor(p/2)], +p/2 kept for even p */
+static int32_t sym_mod_i64(int64_t a, int32_t p) {
+    int64_t r = a % p;
+    if (r < 0) r += p;
+    if (r > p / 2) r -= p;
+    return (int32_t)r;
+}
+
+/* decompose a finite double: |x| = mant * 2^e2, mant integer < 2^53 */
+static void decompose(double x, int *neg, uint64_t *mant, int *e2) {
+    uint64_t bits;
+    memcpy(&bits, &x, 8);
+    *neg        = (int)(bits >> 63);
+    int ebits   = (int)((bits >> 52) & 0x7FF);
+    uint64_t fr = bits & 0xFFFFFFFFFFFFFull;
+    if (ebits == 0) {
+        *mant = fr;
+        *e2   = -1074;
+    } else {
+        *mant = fr | (1ull << 52);
+        *e2   = ebits - 1075;
+    }
+}
+
+/* residue of trunc(x * 2^s) modulo p, symmetric representative (scaling.hpp:99-235 + mod.hpp) */
+static int32_t trunc_scal_mod(double x, int s, int32_t p) {
+    int neg, e2;
+    uint64_t mant;
+    decompose(x, &neg, &mant, &e2);
+    if (mant == 0) return 0;
+    int sh = e2 + s;
+    int64_t r;
+    if (sh <= 0) {
+        uint64_t v = (-sh >= 64) ? 0 : (mant >> (-sh)); /* truncation toward zero of the magnitude */
+        r          = (int64_t)(v % (uint64_t)p);
+    } else {
+        /* mant * 2^sh mod p without overflow: reduce, then multiply by 2^sh mod p stepwise */
+        u128 v = (u128)(mant % (uint64_t)p);
+        while (sh > 0) {
+            int step = sh > 60 ? 60 : sh;
+            v        = (v << step) % (u128)p;
+            sh -= step;
+        }
+        r = (int64_t)v;
+    }
+    if (neg) r = -r;
+    return sym_mod_i64(r, p);
+}
+
+static int ilogb_nz(double x) { return x == 0.0 ? 0 : ilogb(x); } /* template_math.hpp:96-97 */
+
+/* element (row i of op(A), inner index l) of a column-major matrix with leading dimension ld */
+static inline double elem_d(const double *A, size_t ld, int trans, size_t i, size_t l) {
+    return trans ? A[i * ld + l] : A[l * ld + i];
+}
+static inline float elem_f(const float *A, size_t ld, int trans, size_t i, size_t l) {
+    return trans ? A[i * ld + l] : A[l * ld + i];
+}
+
+/* ---------------------------------------------------------------- shifts */
+
+/* rows: number of rows of op(X) (m for A, n for B^T view); inner: k.  For B pass trans = !(op_B==N)
+ * flipped by the caller so that "row i, inner l" addresses op(B)(l, i). */
+void g8o_amax_d(const double *X, size_t ld, int trans, size_t rows, size_t inner, double *amax) {
+    for (size_t i = 0; i < rows; ++i) {
+        double a = 0.0;
+        for (size_t l = 0; l < inner; ++l) a = fmax(a, fabs(elem_d(X, ld, trans, i, l)));
+        amax[i] = a;
+    }
+}
+void g8o_amax_f(const float *X, size_t ld, int trans, size_t rows, size_t inner, float *amax) {
+    for (size_t i = 0; i < rows; ++i) {
+        float a = 0.0f;
+        for (size_t l = 0; l < inner; ++l) a = fmaxf(a, fabsf(elem_f(X, ld, trans, i, l)));
+        amax[i] = a;
+    }
+}
+
+/* ceil(|a| * 2^s) as int8 (scaling.hpp:3-46), restated at the bit level so that the reference's
+ * corner cases are kept: values that scale below one unit give 1, exact integers are not rounded, and
+ * SUBNORMAL inputs are normalised as mant = (frac << k) | 2^prec with k = clz(frac) - (bits - prec),
+ * i.e. the leading fraction bit lands one place below the implicit one (a loose but valid upper bound). */
+static int8_t upper_bound_bits(uint64_t frac, int exp_biased, int prec, int bias, int bits, int s) {
+    if (exp_biased == 0 && frac == 0) return 0;
+    uint64_t mant;
+    int e;
+    if (exp_biased) {
+        mant = frac | (1ull << prec);
+        e    = exp_biased - bias;
+    } else {
+        int clz = (bits == 64) ? __builtin_clzll(frac) : (__builtin_clzll(frac) - 32);
+        int k   = clz - (bits - prec);
+        mant    = (frac << k) | (1ull << prec);
+        e       = (1 - bias) - k;
+    }
+    e += s;
+    int shift = prec - e;
+    if (shift <= 0) return (shift > -64) ? (int8_t)(mant << (-shift)) : 0;
+    if (shift >= prec + 1) return (int8_t)1;
+    uint64_t mask = (1ull << shift) - 1;
+    return (int8_t)((mant >> shift) + ((mant & mask) != 0));
+}
+int8_t g8o_upper_bound_i8_d(double a, int s) {
+    uint64_t b;
+    memcpy(&b, &a, 8);
+    return upper_bound_bits(b & 0xFFFFFFFFFFFFFull, (int)((b >> 52) & 0x7FF), 52, 1023, 64, s);
+}
+int8_t g8o_upper_bound_i8_f(float a, int s) {
+    uint32_t b;
+    memcpy(&b, &a, 4);
+    return upper_bound_bits(b & 0x7FFFFFu, (int)((b >> 23) & 0xFF), 23, 127, 32, s);
+}
+
+/* bound planes of accurate mode: Abar[r*k_pad + l] = ceil(|op(X)(r,l)| * 2^{s0[r]}), zero padded */
+void g8o_extract_d(const double *X, size_t ld, int trans, size_t rows, size_t inner, size_t k_pad, const int16_t *s0,
+                   int8_t *plane) {
+    for (size_t r = 0; r < rows; ++r)
+        for (size_t l = 0; l < k_pad; ++l)
+            plane[r * k_pad + l] = (l < inner) ? g8o_upper_bound_i8_d(elem_d(X, ld, trans, r, l), s0[r]) : 0;
+}
+void g8o_extract_f(const float *X, size_t ld, int trans, size_t rows, size_t inner, size_t k_pad, const int16_t *s0,
+                   int8_t *plane) {
+    for (size_t r = 0; r < rows; ++r)
+        for (size_t l = 0; l < k_pad; ++l)
+            plane[r * k_pad + l] = (l < inner) ? g8o_upper_bound_i8_f(elem_f(X, ld, trans, r, l), s0[r]) : 0;
+}
+
+/* accurate mode, stage (iii): floor( fmaf_rd(-0x1.000006p-1f, log2f(float(max)), log2P) )
+ * (scaling_accu_real.hpp:6-11).  CPU log2 in long double; flag near-integer arguments. */
+int32_t g8o_accu_shift(int32_t cmax, float log2P, int *ambiguous) {
+    float xf = (float)cmax; /* __int2float_rn */
+    if (xf <= 0.0f) {
+        if (ambiguous) *ambiguous = 1; /* log2(0) = -inf: device result is saturated garbage; row is all-zero */
+        return 0;
+    }
+    long double t = (long double)log2P - (long double)0x1.000006p-1f * log2l((long double)xf);
+    long double f = floorl(t);
+    if (ambiguous) *ambiguous = (t - f < 0x1p-12L) || (f + 1 - t < 0x1p-12L);
+    return (int32_t)f;
+}
+
+/* fast mode (scaling_fast_real.hpp:6-22): sft = floor(log2P - 1.5 - max(1, 0.5000001*log2(sumsq))) - ilogb(amax)
+ * `sumsq` is the round-up sum of squares supplied by the caller (order-dependent on the device). */
+int32_t g8o_fast_shift(double amax, double sumsq, float log2P, int is_float, int *ambiguous) {
+    if (sumsq <= 0.0) {
+        if (ambiguous) *ambiguous = 1;
+        return 0;
+    }
+    long double L = log2l((long double)sumsq);
+    long double h = (long double)0x1.000006p-1f * L;
+    if (h < 1.0L) h = 1.0L;
+    long double t = (long double)log2P - 1.5L - h;
+    long double f = floorl(t);
+    if (ambiguous) *ambiguous = (t - f < 0x1p-10L) || (f + 1 - t < 0x1p-10L);
+    int il = is_float ? (amax == 0.0 ? 0 : ilogbf((float)amax)) : ilogb_nz((double)(float)amax);
+    /* reference: Tilogb<float>(amax) -- amax converted to float on the double path too (scaling_fast_real.hpp:13) */
+    return (int32_t)f - il;
+}
+
+/* round-up sum of squares in the device's order is NOT restated here (see header NOTE); this gives the
+ * correctly-rounded-up sequential sum, a tight stand-in used only for the ambiguity-tolerant shift check. */
+double g8o_sumsq_ru_d(const double *X, size_t ld, int trans, size_t i, size_t inner) {
+    int old = fegetround();
+    fesetround(FE_UPWARD);
+    volatile double s = 0.0;
+    for (size_t l = 0; l < inner; ++l) {
+        double v = elem_d(X, ld, trans, i, l);
+        s        = fma(v, v, s);
+    }
+    fesetround(old);
+    return s;
+}
+
+/* ---------------------------------------------------------------- split */
+
+/* planes[i][r * k_pad + l] = int8( trunc(op(X)(r, l) * 2^{-sft[r]}) mod p_i ), zero for l >= inner.
+ * Layout = the reference's A_lo / B_lo: K-major, leading dimension k_pad (gemmul8_real.hpp:95-104). */
+void g8o_split_d(const double *X, size_t ld, int trans, size_t rows, size_t inner, size_t k_pad, const int16_t *sft,
+                 const int32_t *moduli, int num_moduli, int8_t *planes, size_t plane_stride) {
+    for (int i = 0; i < num_moduli; ++i)
+        for (size_t r = 0; r < rows; ++r) {
+            int8_t *dst = planes + (size_t)i * plane_stride + r * k_pad;
+            for (size_t l = 0; l < k_pad; ++l)
+                dst[l] = (l < inner) ? (int8_t)trunc_scal_mod(elem_d(X, ld, trans, r, l), -(int)sft[r], moduli[i]) : 0;
+        }
+}
+void g8o_split_f(const float *X, size_t ld, int trans, size_t rows, size_t inner, size_t k_pad, const int16_t *sft,
+                 const int32_t *moduli, int num_moduli, int8_t *planes, size_t plane_stride) {
+    for (int i = 0; i < num_moduli; ++i)
+        for (size_t r = 0; r < rows; ++r) {
+            int8_t *dst = planes + (size_t)i * plane_stride + r * k_pad;
+            for (size_t l = 0; l < k_pad; ++l)
+                dst[l] = (l < inner) ? (int8_t)trunc_scal_mod((double)elem_f(X, ld, trans, r, l), -(int)sft[r], moduli[i]) : 0;
+        }
+}
+
+/* ---------------------------------------------------------------- exact GEMM + requantise */
+
+/* C_mid[i][c * ldc + r] = int8( sym( sum_l A_lo[i][r*k_pad+l] * B_lo[i][c*k_pad+l]  mod p_i ) )
+ * (gemmul8_real.hpp:150-189, conv_hi2mid_real.hpp:19-22; p = 256 keeps +128 -> int8 -128 as the reference). */
+void g8o_gemm_mod_i8(const int8_t *A_lo, size_t strideA, const int8_t *B_lo, size_t strideB, size_t m, size_t n,
+                     size_t k_pad, const int32_t *moduli, int num_moduli, int8_t *C_mid, size_t ldc, size_t strideC) {
+    for (int i = 0; i < num_moduli; ++i)
+        for (size_t c = 0; c < n; ++c)
+            for (size_t r = 0; r < m; ++r) {
+                const int8_t *a = A_lo + (size_t)i * strideA + r * k_pad;
+                const int8_t *b = B_lo + (size_t)i * strideB + c * k_pad;
+                int64_t acc     = 0;
+                for (size_t l = 0; l < k_pad; ++l) acc += (int32_t)a[l] * (int32_t)b[l];
+                C_mid[(size_t)i * strideC + c * ldc + r] = (int8_t)sym_mod_i64(acc, moduli[i]);
+            }
+}
+
+/* raw int32 product of one plane (bound GEMM of accurate mode, scaling_accu_real.hpp:415-432) */
+void g8o_gemm_i32(const int8_t *A_lo, const int8_t *B_lo, size_t m, size_t n, size_t k_pad, int32_t *C, size_t ldc) {
+    for (size_t c = 0; c < n; ++c)
+        for (size_t r = 0; r < m; ++r) {
+            int64_t acc = 0;
+            for (size_t l = 0; l < k_pad; ++l) acc += (int32_t)A_lo[r * k_pad + l] * (int32_t)B_lo[c * k_pad + l];
+            C[c * ldc + r] = (int32_t)acc;
+        }
+}
+
+/* ---------------------------------------------------------------- CRT + unscale + alpha/beta */
+
+/* mode: 0 -> C = AB; 1 -> C += AB; 2 -> C = -AB; 3 -> C -= AB; 4 -> C = fma(beta, C, alpha*AB)
+ * (inverse_scaling_real.hpp:171-186,117 and template_math.hpp:62-63).
+ * use_dd: 0 = single-double accumulator with qPi1 (T float or N <= P_is_double), 1 = hi/lo with qPi2. */
+static double crt_value(const int8_t *Cmid, size_t stride, int num_moduli, int use_dd, const double *qPi1,
+                        const double *qPi2, const double *P, double invP) {
+    if (!use_dd) {
+        double s = 0.0;
+        for (int i = 0; i < num_moduli; ++i) s = fma(qPi1[i], (double)Cmid[(size_t)i * stride], s);
+        double q = rint(invP * s);
+        return fma(P[0], q, s);
+    }
+    double hi = 0.0, lo = 0.0;
+    for (int i = 0; i < num_moduli; ++i) {
+        double c = (double)Cmid[(size_t)i * stride];
+        hi       = fma(qPi2[2 * i], c, hi);
+        lo       = fma(qPi2[2 * i + 1], c, lo);
+    }
+    double q = rint(invP * hi);
+    return fma(P[1], q, fma(P[0], q, hi) + lo);
+}
+
+void g8o_crt_d(const int8_t *C_mid, size_t ldmid, size_t strideC, size_t m, size_t n, int num_moduli, int use_dd,
+               const double *qPi1, const double *qPi2, const double *P, double invP, const int16_t *sftA,
+               const int16_t *sftB, int mode, double alpha, double beta, double *C, size_t ldc) {
+    for (size_t c = 0; c < n; ++c)
+        for (size_t r = 0; r < m; ++r) {
+            double v  = crt_value(C_mid + c * ldmid + r, strideC, num_moduli, use_dd, qPi1, qPi2, P, invP);
+            double AB = scalbn(v, (int)sftA[r] + (int)sftB[c]);
+            double *o = C + c * ldc + r;
+            switch (mode) {
+            case 0: *o = AB; break;
+            case 1: *o = *o + AB; break;
+            case 2: *o = -AB; break;
+            case 3: *o = *o - AB; break;
+            default: *o = fma(beta, *o, alpha * AB); break;
+            }
+        }
+}
+
+void g8o_crt_f(const int8_t *C_mid, size_t ldmid, size_t strideC, size_t m, size_t n, int num_moduli,
+               const double *qPi1, const double *P, double invP, const int16_t *sftA, const int16_t *sftB, int mode,
+               float alpha, float beta, float *C, size_t ldc) {
+    for (size_t c = 0; c < n; ++c)
+        for (size_t r = 0; r < m; ++r) {
+            double v = crt_value(C_mid + c * ldmid + r, strideC, num_moduli, 0, qPi1, NULL, P, invP);
+            float AB = scalbnf((float)v, (int)sftA[r] + (int)sftB[c]); /* cast BEFORE scalbn (inverse_scaling_real.hpp:72) */
+            float *o = C + c * ldc + r;
+            switch (mode) {
+            case 0: *o = AB; break;
+            case 1: *o = *o + AB; break;
+            case 2: *o = -AB; break;
+            case 3: *o = *o - AB; break;
+            default: *o = fmaf(beta, *o, alpha * AB); break;
+            }
+        }
+}
+
+/* ---------------------------------------------------------------- complex (3M) requantise + CRT */
+
+/* C_mid (re,im interleaved int8 pairs, conv_hi2mid_complex.hpp:75-92):
+ *   re = sym( (ArBr - AiBi) mod p ),  im = sym( (ArBi + AiBr) mod p )
+ * computed directly from the Re/Im planes (the reference's Karatsuba form is the same integer mod p). */
+void g8o_gemm_mod_i8_cplx(const int8_t *Ar, const int8_t *Ai, size_t strideA, const int8_t *Br, const int8_t *Bi,
+                          size_t strideB, size_t m, size_t n, size_t k_pad, const int32_t *moduli, int num_moduli,
+                          int8_t *C_mid, size_t ldc, size_t strideC) {
+    for (int i = 0; i < num_moduli; ++i)
+        for (size_t c = 0; c < n; ++c)
+            for (size_t r = 0; r < m; ++r) {
+                const int8_t *ar = Ar + (size_t)i * strideA + r * k_pad, *ai = Ai + (size_t)i * strideA + r * k_pad;
+                const int8_t *br = Br + (size_t)i * strideB + c * k_pad, *bi = Bi + (size_t)i * strideB + c * k_pad;
+                int64_t re = 0, im = 0;
+                for (size_t l = 0; l < k_pad; ++l) {
+                    re += (int32_t)ar[l] * br[l] - (int32_t)ai[l] * bi[l];
+                    im += (int32_t)ar[l] * bi[l] + (int32_t)ai[l] * br[l];
+                }
+                int8_t *o = C_mid + ((size_t)i * strideC + c * ldc + r) * 2;
+                o[0]      = (int8_t)sym_mod_i64(re, moduli[i]);
+                o[1]      = (int8_t)sym_mod_i64(im, moduli[i]);
+            }
+}
+
+/* complex CRT (inverse_scaling_complex.hpp): the real chain applied to re and im separately, then
+ * mode 0..3 as above componentwise, mode 4 = complex alpha*AB + beta*C with the FMA order of
+ * template_math.hpp:64-75. C is interleaved (re,im). is_float: cast to float before scalbn. */
+void g8o_crt_z(const int8_t *C_mid, size_t ldmid, size_t strideC, size_t m, size_t n, int num_moduli, int use_dd,
+               const double *qPi1, const double *qPi2, const double *P, double invP, const int16_t *sftA,
+               const int16_t *sftB, int mode, const double *alpha, const double *beta, double *C, size_t ldc) {
+    for (size_t c = 0; c < n; ++c)
+        for (size_t r = 0; r < m; ++r) {
+            const int8_t *src = C_mid + (c * ldmid + r) * 2;
+            double vr = crt_value(src, strideC * 2, num_moduli, use_dd, qPi1, qPi2, P, invP);
+            double vi = crt_value(src + 1, strideC * 2, num_moduli, use_dd, qPi1, qPi2, P, invP);
+            int s     = (int)sftA[r] + (int)sftB[c];
+            double xr = scalbn(vr, s), xi = scalbn(vi, s);
+            double *o = C + (c * ldc + r) * 2;
+            switch (mode) {
+            case 0: o[0] = xr; o[1] = xi; break;
+            case 1: o[0] += xr; o[1] += xi; break;
+            case 2: o[0] = -xr; o[1] = -xi; break;
+            case 3: o[0] -= xr; o[1] -= xi; break;
+            default: {
+                double ar = alpha[0], ai = alpha[1], br = beta[0], bi = beta[1], yr = o[0], yi = o[1];
+                o[0] = fma(-bi, yi, fma(br, yr, fma(-ai, xi, ar * xr)));
+                o[1] = fma(bi, yr, fma(br, yi, fma(ai, xr, ar * xi)));
+            }
+            }
+        }
+}
+
+void g8o_crt_c(const int8_t *C_mid, size_t ldmid, size_t strideC, size_t m, size_t n, int num_moduli,
+               const double *qPi1, const double *P, double invP, const int16_t *sftA, const int16_t *sftB, int mode,
+               const float *alpha, const float *beta, float *C, size_t ldc) {
+    for (size_t c = 0; c < n; ++c)
+        for (size_t r = 0; r < m; ++r) {
+            const int8_t *src = C_mid + (c * ldmid + r) * 2;
+            double vr = crt_value(src, strideC * 2, num_moduli, 0, qPi1, NULL, P, invP);
+            double vi = crt_value(src + 1, strideC * 2, num_moduli, 0, qPi1, NULL, P, invP);
+            int s     = (int)sftA[r] + (int)sftB[c];
+            float xr = scalbnf((float)vr, s), xi = scalbnf((float)vi, s);
+            float *o = C + (c * ldc + r) * 2;
+            switch (mode) {
+            case 0: o[0] = xr; o[1] = xi; break;
+            case 1: o[0] += xr; o[1] += xi; break;
+            case 2: o[0] = -xr; o[1] = -xi; break;
+            case 3: o[0] -= xr; o[1] -= xi; break;
+            default: {
+                float ar = alpha[0], ai = alpha[1], br = beta[0], bi = beta[1], yr = o[0], yi = o[1];
+                o[0] = fmaf(-bi, yi, fmaf(br, yr, fmaf(-ai, xi, ar * xr)));
+                o[1] = fmaf(bi, yr, fmaf(br, yi, fmaf(ai, xr, ar * xi)));
+            }
+            }
+        }
+}
