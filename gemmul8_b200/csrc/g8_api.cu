@@ -1,0 +1,288 @@
+// gemmul8_b200 -- C-ABI orchestrator (include/gemmul8_c.h): workspace carving + the three-stage pipeline.
+//
+// Mirrors the control flow of reference real::gemm / complex::gemm (gemmul8_real.hpp:53-211,
+// gemmul8_complex.hpp:53-226) with these deliberate differences:
+//   * one persistent tcgen05 launch covers all moduli, mod-p is fused into its epilogue (no C_hi, no conv_hi2mid);
+//   * accurate mode never materialises the bound product: its GEMM epilogue reduces row/col maxima directly;
+//   * no host synchronisation unless the caller asks for the phase timings;
+//   * constants live in static __constant__ memory (no per-call cudaMemcpyToSymbol, table.hpp:854-862).
+// The workspace layout (A_lo | sftA | B_lo | sftB | C_mid | scratch) is byte-compatible with the reference's.
+#include "g8_internal.cuh"
+#include "../../include/gemmul8_c.h"
+
+#include <algorithm>
+#include <cstdio>
+
+namespace g8 {
+
+struct Sizes {
+    size_t k_pad, m_pad, n_pad, sizeA, sizeB, sizeC;
+    unsigned num_mat;
+    size_t low, mid, hi;      // bytes per element of the low / mid / hi types
+    unsigned cplx3, num_C_hi; // 3 for complex (three plane groups), C_hi planes
+    size_t totalA, totalB, totalC;
+};
+
+static unsigned num_mat(int backend, unsigned n) { // table.hpp:69-75
+    if (backend == INT8) return n;
+    return n <= 6 ? 2 * n : 12 + 3 * (n - 6);
+}
+
+static Sizes sizes(bool cplx, int backend, size_t m, size_t n, size_t k, unsigned N, bool enA, bool enB) {
+    Sizes s{};
+    s.k_pad = pad256(k), s.m_pad = pad256(m), s.n_pad = pad256(n);
+    s.sizeA = s.k_pad * s.m_pad, s.sizeB = s.k_pad * n, s.sizeC = s.m_pad * n;
+    s.num_mat = num_mat(backend, N);
+    s.low = 1, s.mid = (backend == INT8 ? 1 : 2) * (cplx ? 2 : 1), s.hi = 4;
+    s.cplx3    = cplx ? 3 : 1;
+    s.num_C_hi = (backend == INT8 ? 1 : 3) * s.cplx3;
+    const size_t lwork = size_t(1) << 25; // 32 MiB reserved by the reference for cuBLASLt (gemmul8_real.hpp:32)
+    s.totalA = 255 + s.low * s.sizeA * (s.num_mat + (enA ? 1 : 0)) * s.cplx3 + sizeof(int16_t) * s.m_pad;
+    s.totalB = 255 + s.low * s.sizeB * (s.num_mat + (enB ? 1 : 0)) * s.cplx3 + sizeof(int16_t) * s.n_pad;
+    s.totalC = 255 + s.mid * s.sizeC * (N - 1) + std::max(lwork, s.mid * s.sizeC) + s.hi * s.sizeC * s.num_C_hi;
+    return s;
+}
+
+struct PhaseTimer {
+    cudaEvent_t ev[5]{};
+    cudaStream_t st;
+    bool on;
+    PhaseTimer(bool enable, cudaStream_t s) : st(s), on(enable) {
+        if (on)
+            for (auto &e : ev) cudaEventCreate(&e);
+    }
+    void mark(int i) {
+        if (on) cudaEventRecord(ev[i], st);
+    }
+    void finish(double *ns) {
+        if (!on) return;
+        cudaEventSynchronize(ev[4]);
+        float ms;
+        cudaEventElapsedTime(&ms, ev[0], ev[1]); ns[0] = ms * 1e6;
+        cudaEventElapsedTime(&ms, ev[1], ev[2]); ns[1] = ms * 1e6;
+        ns[2] = 0.0; // requantisation is fused into the GEMM epilogue
+        cudaEventElapsedTime(&ms, ev[2], ev[4]); ns[3] = ms * 1e6;
+        for (auto &e : ev) cudaEventDestroy(e);
+    }
+};
+
+static bool device_ok() {
+    static int ok = -1;
+    if (ok < 0) {
+        int dev = 0, major = 0, minor = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return false;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+        cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+        ok = (major == 10 && minor == 0) ? 1 : 0;
+    }
+    return ok == 1;
+}
+
+static SplitArgs split_args(int is_A, int op, size_t rows, size_t k, const void *X, size_t ld, unsigned N, int16_t *sft,
+                            int8_t *base, size_t plane_stride, size_t group_stride_planes) {
+    SplitArgs a{};
+    a.X = X, a.ld = ld, a.rows = rows, a.inner = k, a.k_pad = pad256(k), a.sft = sft;
+    for (int g = 0; g < 3; ++g) a.planes[g] = base + g * group_stride_planes * plane_stride;
+    a.plane_stride = plane_stride;
+    a.num_moduli   = (int)N;
+    // A: op N -> element (r,l) at A[l*lda + r] (row-strided); op T/C -> row r contiguous.  B: the other way round.
+    a.row_contig = is_A ? (op != OP_N) : (op == OP_N);
+    a.conj       = (op == OP_C);
+    return a;
+}
+
+static int gemm_impl(const g8_gemm_desc &d, double *phase_ns) {
+    if (!d.A || !d.B || !d.C || !d.alpha || !d.beta || !d.work) return G8_STATUS_INVALID_VALUE;
+    if (d.dtype < F32 || d.dtype > C64 || d.op_A < 0 || d.op_A > 2 || d.op_B < 0 || d.op_B > 2) return G8_STATUS_INVALID_VALUE;
+    if (d.num_moduli < 2 || d.num_moduli > G8_MAX_MODULI) return G8_STATUS_INVALID_VALUE;
+    if (d.backend != INT8) return G8_STATUS_NOT_SUPPORTED;
+    if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
+    if (d.m == 0 || d.n == 0) return 0;
+
+    const bool cplx   = d.dtype >= C32;
+    const unsigned N  = d.num_moduli;
+    const bool enA = d.enable_skip_scalA, enB = d.enable_skip_scalB;
+    const bool skipA = d.skip_scalA && enA, skipB = d.skip_scalB && enB;
+    const Sizes s  = sizes(cplx, d.backend, d.m, d.n, d.k, N, enA, enB);
+    cudaStream_t st = static_cast<cudaStream_t>(d.stream);
+
+    // ---- workspace (gemmul8_real.hpp:95-107 / gemmul8_complex.hpp:95-118) ----
+    const size_t groupA_planes = s.num_mat, groupB_planes = s.num_mat; // planes between Re / Im / Re+Im groups
+    int8_t *wk  = static_cast<int8_t *>(align256(d.work));
+    int8_t *wkA = d.workA ? static_cast<int8_t *>(align256(d.workA)) : nullptr;
+    int8_t *wkB = d.workB ? static_cast<int8_t *>(align256(d.workB)) : nullptr;
+    int8_t *A_lo  = wkA ? wkA : wk;
+    int16_t *sftA = reinterpret_cast<int16_t *>(A_lo + s.sizeA * (s.num_mat + (enA ? 1 : 0)) * s.cplx3);
+    int8_t *afterA = reinterpret_cast<int8_t *>(sftA + s.m_pad);
+    int8_t *B_lo  = wkB ? wkB : (wkA ? wk : afterA);
+    int16_t *sftB = reinterpret_cast<int16_t *>(B_lo + s.sizeB * (s.num_mat + (enB ? 1 : 0)) * s.cplx3);
+    int8_t *afterB = reinterpret_cast<int8_t *>(sftB + s.n_pad);
+    int8_t *C_mid = wkB ? (wkA ? wk : afterA) : afterB;
+    int8_t *scratch = C_mid + s.mid * s.sizeC * N; // beyond the last C_mid plane: the reference's Lt workspace + C_hi
+    const size_t scratch_avail = s.totalC - 255 - s.mid * s.sizeC * N;
+    // bound planes of accurate mode: the extra plane(s) when skipping is enabled, else alias plane 0 (gemmul8_real.hpp:131-132)
+    int8_t *A_bound = A_lo + (enA ? s.sizeA * s.num_mat * s.cplx3 : 0);
+    int8_t *B_bound = B_lo + (enB ? s.sizeB * s.num_mat * s.cplx3 : 0);
+
+    PhaseTimer tm(phase_ns != nullptr, st);
+    tm.mark(0);
+
+    // ---- stage 1: shifts + split ----
+    if (d.k == 0) {
+        cudaMemsetAsync(C_mid, 0, s.mid * s.sizeC * N, st);
+        cudaMemsetAsync(sftA, 0, sizeof(int16_t) * s.m_pad, st);
+        cudaMemsetAsync(sftB, 0, sizeof(int16_t) * s.n_pad, st);
+    } else if (!(skipA && skipB)) {
+        SplitArgs sa = split_args(1, d.op_A, d.m, d.k, d.A, d.lda, N, sftA, A_lo, s.sizeA, groupA_planes);
+        SplitArgs sb = split_args(0, d.op_B, d.n, d.k, d.B, d.ldb, N, sftB, B_lo, s.sizeB, groupB_planes);
+        if (d.fastmode) {
+            if (!skipA) launch_split(sa, d.dtype, 1, st);
+            if (!skipB) launch_split(sb, d.dtype, 1, st);
+        } else {
+            const size_t need = sizeof(int32_t) * (s.m_pad + s.n_pad);
+            if (need > scratch_avail) return G8_STATUS_NOT_SUPPORTED;
+            int32_t *rowmax = reinterpret_cast<int32_t *>(scratch), *colmax = rowmax + s.m_pad;
+            SplitArgs ea = sa, eb = sb;
+            for (int g = 0; g < 3; ++g) ea.planes[g] = A_bound + g * s.sizeA, eb.planes[g] = B_bound + g * s.sizeB;
+            if (!skipA) launch_split(ea, d.dtype, 2, st);
+            if (!skipB) launch_split(eb, d.dtype, 2, st);
+            cudaMemsetAsync(rowmax, 0, need, st);
+            GemmArgs g{};
+            g.A = A_bound, g.B = B_bound, g.strideA = s.sizeA, g.strideB = s.sizeB;
+            g.m = d.m, g.n = d.n, g.m_pad = s.m_pad, g.k_pad = s.k_pad;
+            g.num_units = 1, g.first_modulus = 0;
+            g.epi = cplx ? EPI_BOUND_MAX_CPLX : EPI_BOUND_MAX;
+            g.groupA[0] = 0, g.groupA[1] = 1, g.groupA[2] = 2;
+            g.groupB[0] = 0, g.groupB[1] = 1, g.groupB[2] = 2;
+            if (!cplx) g.groupA[1] = g.groupA[2] = g.groupB[1] = g.groupB[2] = 0;
+            g.ldc = s.m_pad, g.rowmax = rowmax, g.colmax = colmax;
+            if (int e = launch_gemm_tc(g, st)) return e;
+            if (!skipA) {
+                launch_finalize_accu_shift(sftA, rowmax, d.m, (int)N, st);
+                launch_split(sa, d.dtype, 0, st);
+            }
+            if (!skipB) {
+                launch_finalize_accu_shift(sftB, colmax, d.n, (int)N, st);
+                launch_split(sb, d.dtype, 0, st);
+            }
+        }
+    }
+    tm.mark(1);
+
+    // ---- stage 2: all moduli in one persistent tensor-core launch, mod-p fused ----
+    if (d.k != 0) {
+        GemmArgs g{};
+        g.A = A_lo, g.B = B_lo, g.strideA = s.sizeA, g.strideB = s.sizeB;
+        g.m = d.m, g.n = d.n, g.m_pad = s.m_pad, g.k_pad = s.k_pad;
+        g.num_units = (int)N, g.first_modulus = 0;
+        g.epi = cplx ? EPI_MOD_I8_CPLX : EPI_MOD_I8;
+        for (int i = 0; i < 3; ++i) g.groupA[i] = cplx ? i * (int)groupA_planes : 0, g.groupB[i] = cplx ? i * (int)groupB_planes : 0;
+        g.out = C_mid, g.out_stride = s.sizeC, g.ldc = s.m_pad;
+        if (int e = launch_gemm_tc(g, st)) return e;
+    }
+    tm.mark(2);
+
+    // ---- stage 3: CRT + unscale + alpha/beta ----
+    CrtArgs c{};
+    c.C_mid = C_mid, c.ldmid = s.m_pad, c.plane_stride = s.sizeC, c.m = d.m, c.n = d.n, c.num_moduli = (int)N;
+    c.C = d.C, c.ldc = d.ldc, c.sftA = sftA, c.sftB = sftB, c.alpha = d.alpha, c.beta = d.beta;
+    if (int e = launch_crt(c, d.dtype, st)) return e;
+    tm.mark(4);
+    tm.finish(phase_ns);
+    return (int)cudaPeekAtLastError();
+}
+
+// C_hi (int32, summed over K-shards) -> symmetric residues
+__global__ void requant_i32_kernel(const int32_t *__restrict__ C_hi, size_t count4, int first_modulus, int8_t *__restrict__ C_mid) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count4) return;
+    const int u     = blockIdx.y;
+    const int32_t p = g8d_moduli[INT8][first_modulus + u], pinv = g8d_pinv32[INT8][first_modulus + u];
+    const int4 v    = reinterpret_cast<const int4 *>(C_hi)[(size_t)u * count4 + i];
+    const int32_t a = mod_i32(v.x, p, pinv), b = mod_i32(v.y, p, pinv), c = mod_i32(v.z, p, pinv), e = mod_i32(v.w, p, pinv);
+    reinterpret_cast<uint32_t *>(C_mid)[(size_t)u * count4 + i] =
+        (uint32_t)(a & 0xFF) | ((uint32_t)(b & 0xFF) << 8) | ((uint32_t)(c & 0xFF) << 16) | ((uint32_t)e << 24);
+}
+
+} // namespace g8
+
+using namespace g8;
+
+extern "C" {
+
+__attribute__((visibility("default"))) size_t g8_work_size(int is_complex, int backend, size_t m, size_t n, size_t k, unsigned num_moduli, int enA, int enB,
+                    size_t *workSizeA, size_t *workSizeB) {
+    const Sizes s = sizes(is_complex != 0, backend, m, n, k, num_moduli, enA != 0, enB != 0);
+    if (workSizeA) *workSizeA = s.totalA;
+    if (workSizeB) *workSizeB = s.totalB;
+    return s.totalA + s.totalB + s.totalC;
+}
+
+__attribute__((visibility("default"))) int g8_gemm(const g8_gemm_desc *d, double *phase_ns) {
+    if (!d) return G8_STATUS_INVALID_VALUE;
+    if (phase_ns) phase_ns[0] = phase_ns[1] = phase_ns[2] = phase_ns[3] = 0.0;
+    return gemm_impl(*d, phase_ns);
+}
+
+__attribute__((visibility("default"))) int g8_stage_split(int dtype, int is_A, int op, size_t rows, size_t k, const void *X, size_t ld, unsigned num_moduli, int mode,
+                   int16_t *sft, int8_t *planes, size_t plane_stride_bytes, size_t group_stride_planes, void *stream) {
+    if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
+    if (!X || !sft || !planes || dtype < F32 || dtype > C64 || num_moduli < 2 || num_moduli > G8_MAX_MODULI) return G8_STATUS_INVALID_VALUE;
+    if (rows == 0 || k == 0) return 0;
+    SplitArgs a = split_args(is_A, op, rows, k, X, ld, num_moduli, sft, planes, plane_stride_bytes, group_stride_planes);
+    if (mode == 2)
+        for (int g = 0; g < 3; ++g) a.planes[g] = planes + g * plane_stride_bytes;
+    launch_split(a, dtype, mode, static_cast<cudaStream_t>(stream));
+    return (int)cudaGetLastError();
+}
+
+__attribute__((visibility("default"))) int g8_stage_finalize_shift(int16_t *sft, const int32_t *cmax, size_t count, unsigned num_moduli, void *stream) {
+    if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
+    if (count == 0) return 0;
+    launch_finalize_accu_shift(sft, cmax, count, (int)num_moduli, static_cast<cudaStream_t>(stream));
+    return (int)cudaGetLastError();
+}
+
+__attribute__((visibility("default"))) int g8_stage_gemm(int epilogue, int use_simt, const int8_t *A_lo, size_t strideA, const int8_t *B_lo, size_t strideB, size_t m, size_t n,
+                  size_t k_pad, int num_units, int first_modulus, const int *groupA, const int *groupB, void *out, size_t out_stride,
+                  size_t ldc, int32_t *rowmax, int32_t *colmax, void *stream) {
+    if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
+    if (!A_lo || !B_lo || k_pad % 256 || epilogue < 0 || epilogue > 4) return G8_STATUS_INVALID_VALUE;
+    GemmArgs g{};
+    g.A = A_lo, g.B = B_lo, g.strideA = strideA, g.strideB = strideB, g.m = m, g.n = n, g.m_pad = pad256(m), g.k_pad = k_pad;
+    g.num_units = num_units, g.first_modulus = first_modulus, g.epi = epilogue;
+    for (int i = 0; i < 3; ++i) g.groupA[i] = groupA ? groupA[i] : 0, g.groupB[i] = groupB ? groupB[i] : 0;
+    g.out = out, g.out_stride = out_stride, g.ldc = ldc, g.rowmax = rowmax, g.colmax = colmax;
+    return use_simt ? launch_gemm_simt(g, static_cast<cudaStream_t>(stream)) : launch_gemm_tc(g, static_cast<cudaStream_t>(stream));
+}
+
+__attribute__((visibility("default"))) int g8_stage_crt(int dtype, const void *C_mid, size_t ldmid, size_t plane_stride, size_t m, size_t n, unsigned num_moduli, void *C,
+                 size_t ldc, const int16_t *sftA, const int16_t *sftB, const void *alpha, const void *beta, void *stream) {
+    if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
+    if (!C_mid || !C || !sftA || !sftB || !alpha || !beta || num_moduli < 2 || num_moduli > G8_MAX_MODULI) return G8_STATUS_INVALID_VALUE;
+    CrtArgs c{};
+    c.C_mid = C_mid, c.ldmid = ldmid, c.plane_stride = plane_stride, c.m = m, c.n = n, c.num_moduli = (int)num_moduli;
+    c.C = C, c.ldc = ldc, c.sftA = sftA, c.sftB = sftB, c.alpha = alpha, c.beta = beta;
+    return launch_crt(c, dtype, static_cast<cudaStream_t>(stream));
+}
+
+__attribute__((visibility("default"))) int g8_stage_requant_i32(const int32_t *C_hi, size_t count_per_plane, int num_units, int first_modulus, int8_t *C_mid, void *stream) {
+    if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
+    if (count_per_plane % 4) return G8_STATUS_INVALID_VALUE;
+    if (count_per_plane == 0 || num_units == 0) return 0;
+    const size_t c4 = count_per_plane / 4;
+    const dim3 grid((unsigned)((c4 + 255) / 256), (unsigned)num_units);
+    requant_i32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(C_hi, c4, first_modulus, C_mid);
+    return (int)cudaGetLastError();
+}
+
+__attribute__((visibility("default"))) const char *g8_version(void) { return "gemmul8_b200 0.1 (sm_100a, tcgen05 kind::i8)"; }
+
+__attribute__((visibility("default"))) int g8_device_supported(int device) {
+    int major = 0, minor = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
+    return major == 10 && minor == 0;
+}
+
+} // extern "C"

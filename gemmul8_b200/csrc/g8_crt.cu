@@ -1,0 +1,203 @@
+// gemmul8_b200 -- stage 3: CRT accumulation, modular fold, unscale and alpha/beta epilogue in one HBM pass.
+//
+// Replaces reference inverse_scaling_real.hpp:8-278 and inverse_scaling_complex.hpp:8-326.
+// The floating-point operation ORDER is contractual for bit parity and is kept exactly:
+//   single chain (T float, or N <= P_is_double):  S = fma(w_i, c_i, S), i ascending; q = rint(invP*S);
+//                                                 r = fma(P.x, q, S)
+//   hi/lo chain (T double, N > P_is_double):      H = fma(w_i.x, c_i, H); L = fma(w_i.y, c_i, L);
+//                                                 q = rint(invP*H); r = fma(P.y, q, fma(P.x, q, H) + L)
+//   AB = scalbn((T)r, sftA[row] + sftB[col]);  then C = AB | C+AB | -AB | C-AB | fma(beta, C, alpha*AB).
+// What changes is the memory access: each thread owns 16 bytes of output (2 doubles / 4 floats / 1 double2 /
+// 2 float2) of one column, so plane loads are contiguous per warp and stores are full 128-bit coalesced,
+// instead of one element per thread with N strided byte loads.
+#include "g8_internal.cuh"
+
+namespace g8 {
+
+template <typename T> struct CrtTraits;
+template <> struct CrtTraits<float>   { using U = float;  static constexpr bool cplx = false; static constexpr int VEC = 4; };
+template <> struct CrtTraits<double>  { using U = double; static constexpr bool cplx = false; static constexpr int VEC = 2; };
+template <> struct CrtTraits<float2>  { using U = float;  static constexpr bool cplx = true;  static constexpr int VEC = 2; };
+template <> struct CrtTraits<double2> { using U = double; static constexpr bool cplx = true;  static constexpr int VEC = 1; };
+
+__device__ __forceinline__ float  scal(float v, int s) { return scalbnf(v, s); }
+__device__ __forceinline__ double scal(double v, int s) { return scalbn(v, s); }
+__device__ __forceinline__ float  fma_(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
+
+struct Scalars {
+    double ar, ai, br, bi; // host scalars widened (exact); used in MODE 4
+};
+
+// MODE: 0 C=AB, 1 C+=AB, 2 C=-AB, 3 C-=AB, 4 general (host scalars), 5 general (device scalars)
+template <typename T, bool DD, int MODE, bool VECIO>
+__global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t groups, size_t total) {
+    using TR           = CrtTraits<T>;
+    using U            = typename TR::U;
+    constexpr int VEC  = TR::VEC;
+    constexpr int NV   = TR::cplx ? 2 * VEC : VEC; // scalar lanes per thread (always 16 bytes of output... or 4/2)
+    const size_t idx   = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const size_t col = idx / groups;
+    const size_t row = (idx - col * groups) * VEC;
+    const int N      = c.num_moduli;
+
+    // ---- accumulate over moduli (i ascending) ----
+    double hi[NV], lo[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) hi[j] = 0.0, lo[j] = 0.0;
+    const int8_t *src = reinterpret_cast<const int8_t *>(c.C_mid) + (col * c.ldmid + row) * (TR::cplx ? 2 : 1);
+    const size_t pstride = c.plane_stride * (TR::cplx ? 2 : 1);
+    const int tbl1 = N - 2, tbl2 = N - thresholds(INT8).P_is_double - 1;
+#pragma unroll 2
+    for (int i = 0; i < N; ++i) {
+        int8_t r[NV];
+        if constexpr (NV == 4) *reinterpret_cast<uint32_t *>(r) = *reinterpret_cast<const uint32_t *>(src + (size_t)i * pstride);
+        else *reinterpret_cast<uint16_t *>(r) = *reinterpret_cast<const uint16_t *>(src + (size_t)i * pstride);
+        if constexpr (DD) {
+            const double wx = g8d_qPi2[INT8][tbl2][i][0], wy = g8d_qPi2[INT8][tbl2][i][1];
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const double cd = (double)r[j];
+                hi[j]           = fma(wx, cd, hi[j]);
+                lo[j]           = fma(wy, cd, lo[j]);
+            }
+        } else {
+            const double w = g8d_qPi1[INT8][tbl1][i];
+#pragma unroll
+            for (int j = 0; j < NV; ++j) hi[j] = fma(w, (double)r[j], hi[j]);
+        }
+    }
+
+    // ---- fold modulo P, cast, unscale ----
+    const double invP = g8d_invP[INT8][N - 2];
+    const double Px = g8d_P[INT8][N - 2][0], Py = g8d_P[INT8][N - 2][1];
+    const int sB = c.sftB[col];
+    U ab[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const size_t rj = row + (TR::cplx ? j / 2 : j);
+        const int sft   = (rj < c.m ? (int)c.sftA[rj] : 0) + sB;
+        const double q  = rint(invP * hi[j]);
+        double r;
+        if constexpr (DD) r = fma(Py, q, fma(Px, q, hi[j]) + lo[j]);
+        else r = fma(Px, q, hi[j]);
+        ab[j] = scal((U)r, sft);
+    }
+
+    // ---- alpha / beta ----
+    U *dst = reinterpret_cast<U *>(c.C) + (col * c.ldc + row) * (TR::cplx ? 2 : 1);
+    const int valid = (int)min((size_t)VEC, c.m - row) * (TR::cplx ? 2 : 1);
+    U old[NV];
+    if constexpr (MODE == 1 || MODE == 3 || MODE >= 4) {
+        if (VECIO && valid == NV) {
+            *reinterpret_cast<uint4 *>(old) = *reinterpret_cast<const uint4 *>(dst);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NV; ++j) old[j] = (j < valid) ? dst[j] : U(0);
+        }
+    }
+    U out[NV];
+    if constexpr (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) out[j] = ab[j];
+    } else if constexpr (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) out[j] = old[j] + ab[j];
+    } else if constexpr (MODE == 2) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) out[j] = -ab[j];
+    } else if constexpr (MODE == 3) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) out[j] = old[j] - ab[j];
+    } else {
+        U ar, ai = 0, br, bi = 0;
+        if constexpr (MODE == 5) {
+            const U *pa = reinterpret_cast<const U *>(c.alpha), *pb = reinterpret_cast<const U *>(c.beta);
+            ar = pa[0], br = pb[0];
+            if constexpr (TR::cplx) ai = pa[1], bi = pb[1];
+        } else {
+            ar = (U)hs.ar, ai = (U)hs.ai, br = (U)hs.br, bi = (U)hs.bi;
+        }
+        if constexpr (TR::cplx) {
+            // Taxpby_scal (template_math.hpp:64-75)
+#pragma unroll
+            for (int j = 0; j < NV; j += 2) {
+                const U xr = ab[j], xi = ab[j + 1], yr = old[j], yi = old[j + 1];
+                out[j]     = fma_(-bi, yi, fma_(br, yr, fma_(-ai, xi, ar * xr)));
+                out[j + 1] = fma_(bi, yr, fma_(br, yi, fma_(ai, xr, ar * xi)));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NV; ++j) out[j] = fma_(br, old[j], ar * ab[j]);
+        }
+    }
+    if (VECIO && valid == NV) {
+        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(out);
+    } else {
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+            if (j < valid) dst[j] = out[j];
+    }
+}
+
+template <typename T, bool DD, int MODE> static void crt_go(const CrtArgs &c, const Scalars &hs, cudaStream_t st) {
+    constexpr int VEC   = CrtTraits<T>::VEC;
+    const size_t groups = (c.m + VEC - 1) / VEC;
+    const size_t total  = groups * c.n;
+    if (total == 0) return;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(c.C) % 16 == 0) && ((c.ldc * sizeof(T)) % 16 == 0);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (vec_ok) crt_kernel<T, DD, MODE, true><<<grid, 256, 0, st>>>(c, hs, groups, total);
+    else crt_kernel<T, DD, MODE, false><<<grid, 256, 0, st>>>(c, hs, groups, total);
+}
+
+template <typename T, bool DD> static void crt_mode(const CrtArgs &c, int mode, const Scalars &hs, cudaStream_t st) {
+    switch (mode) {
+    case 0: crt_go<T, DD, 0>(c, hs, st); break;
+    case 1: crt_go<T, DD, 1>(c, hs, st); break;
+    case 2: crt_go<T, DD, 2>(c, hs, st); break;
+    case 3: crt_go<T, DD, 3>(c, hs, st); break;
+    case 4: crt_go<T, DD, 4>(c, hs, st); break;
+    default: crt_go<T, DD, 5>(c, hs, st); break;
+    }
+}
+
+// alpha/beta residency and special cases follow inverse_scaling_real.hpp:209-237 / _complex.hpp:254-284:
+// device-resident alpha -> general kernel reading the scalars on the device; host scalars -> the four
+// special cases (alpha = +-1, beta in {0,1}) else the general FMA form.
+int launch_crt(const CrtArgs &c, int dtype, cudaStream_t st) {
+    cudaPointerAttributes attr{};
+    cudaError_t e = cudaPointerGetAttributes(&attr, c.alpha);
+    if (e != cudaSuccess) cudaGetLastError(); // plain host pointers may report an error on old drivers: treat as host
+    const bool is_device = (e == cudaSuccess) && attr.type != cudaMemoryTypeUnregistered && attr.type != cudaMemoryTypeHost;
+    Scalars hs{1, 0, 0, 0};
+    int mode = 5;
+    if (!is_device) {
+        switch (dtype) {
+        case F32: hs.ar = *static_cast<const float *>(c.alpha); hs.br = *static_cast<const float *>(c.beta); break;
+        case F64: hs.ar = *static_cast<const double *>(c.alpha); hs.br = *static_cast<const double *>(c.beta); break;
+        case C32: hs.ar = static_cast<const float *>(c.alpha)[0]; hs.ai = static_cast<const float *>(c.alpha)[1];
+                  hs.br = static_cast<const float *>(c.beta)[0];  hs.bi = static_cast<const float *>(c.beta)[1]; break;
+        default:  hs.ar = static_cast<const double *>(c.alpha)[0]; hs.ai = static_cast<const double *>(c.alpha)[1];
+                  hs.br = static_cast<const double *>(c.beta)[0];  hs.bi = static_cast<const double *>(c.beta)[1]; break;
+        }
+        mode = 4;
+        if (hs.ai == 0.0 && hs.bi == 0.0) {
+            if (hs.ar == 1.0 && hs.br == 0.0) mode = 0;
+            else if (hs.ar == 1.0 && hs.br == 1.0) mode = 1;
+            else if (hs.ar == -1.0 && hs.br == 0.0) mode = 2;
+            else if (hs.ar == -1.0 && hs.br == 1.0) mode = 3;
+        }
+    }
+    const bool dd = c.num_moduli > thresholds(INT8).P_is_double;
+    switch (dtype) {
+    case F32: crt_mode<float, false>(c, mode, hs, st); break;
+    case C32: crt_mode<float2, false>(c, mode, hs, st); break;
+    case F64: dd ? crt_mode<double, true>(c, mode, hs, st) : crt_mode<double, false>(c, mode, hs, st); break;
+    default:  dd ? crt_mode<double2, true>(c, mode, hs, st) : crt_mode<double2, false>(c, mode, hs, st); break;
+    }
+    return (int)cudaGetLastError();
+}
+
+} // namespace g8

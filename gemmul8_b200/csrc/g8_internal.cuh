@@ -1,0 +1,72 @@
+// gemmul8_b200 -- internal interfaces between the stage kernels and the C-ABI orchestrator.
+#pragma once
+#include "g8_common.cuh"
+
+namespace g8 {
+
+// ---- stage 1: split -------------------------------------------------------------------------
+struct SplitArgs {
+    const void *X;       // operand (device), column-major
+    size_t ld;           // leading dimension in elements
+    size_t rows;         // rows of the "rows x inner" view (m for A, n for B)
+    size_t inner;        // k
+    size_t k_pad;        // pad256(k) = leading dimension of every plane
+    int16_t *sft;        // shift exponents (see g8_common.cuh for the sign convention)
+    int8_t *planes[3];   // real: planes[0]; complex: Re, Im, (Re+Im) mod p   [or the bound planes in mode 2]
+    size_t plane_stride; // bytes between consecutive moduli
+    int num_moduli;
+    int row_contig;      // 1: row r contiguous along inner; 0: element (r,l) at X[l*ld + r]
+    int conj;            // complex only: conjugate on load (op == C)
+};
+void launch_split(const SplitArgs &a, int dtype, int mode, cudaStream_t st);
+void launch_finalize_accu_shift(int16_t *sft, const int32_t *cmax, size_t count, int num_moduli, cudaStream_t st);
+
+// ---- stage 2: low-precision GEMMs -------------------------------------------------------------
+// One "unit" is one output tile set: for unit u the kernel accumulates `nchain` products
+//   acc[a] += Aplane[chainA[a][c]] (rows x K)^T-major  *  Bplane[chainB[a][c]]
+// and runs the epilogue `epi` on the accumulators.
+enum GemmEpilogue : int {
+    EPI_MOD_I8    = 0, // C_mid[u] = int8( sym( acc0 mod p_u ) )                                   (real)
+    EPI_RAW_I32   = 1, // C_hi[u]  = acc0 (int32), for the K-sharded multi-GPU partials
+    EPI_BOUND_MAX = 2, // rowmax[r] = max(rowmax[r], acc0), colmax[c] likewise                     (accurate, real)
+    EPI_MOD_I8_CPLX   = 3, // C_mid[u] = {sym((acc0 - acc1) mod p), sym((acc2 - acc0 - acc1) mod p)}  (complex 3M)
+    EPI_BOUND_MAX_CPLX = 4, // max over max(acc0, acc1) with acc0 = ArBr + AiBi, acc1 = ArBi + AiBr
+};
+
+struct GemmArgs {
+    const int8_t *A;     // base of A-side planes (k_pad x m_pad each, K-major)
+    const int8_t *B;     // base of B-side planes (k_pad x n each, K-major)
+    size_t strideA;      // bytes between A planes
+    size_t strideB;      // bytes between B planes
+    size_t m, n;         // logical extents (rows of A-side / B-side actually valid)
+    size_t m_pad, k_pad; // padded extents
+    int num_units;       // moduli (or 1 for the bound GEMM)
+    int first_modulus;   // index of unit 0 in the moduli table
+    int epi;
+    // complex: plane group offsets (in planes) of Re / Im / Re+Im inside A and B
+    int groupA[3], groupB[3];
+    void *out;           // C_mid (int8 / int8x2) or C_hi (int32)
+    size_t out_stride;   // elements between output planes
+    size_t ldc;          // leading dimension of the output (m_pad)
+    int32_t *rowmax, *colmax;
+};
+// tcgen05 path (product).  Returns cudaError_t-compatible int.
+int launch_gemm_tc(const GemmArgs &g, cudaStream_t st);
+// plain dp4a path: TEST/DEBUG reference for the tensor-core kernel, never used by g8_gemm().
+int launch_gemm_simt(const GemmArgs &g, cudaStream_t st);
+
+// ---- stage 3: CRT + unscale + alpha/beta ------------------------------------------------------
+struct CrtArgs {
+    const void *C_mid;   // int8 (real) / int8x2 (complex), num_moduli planes
+    size_t ldmid;        // m_pad
+    size_t plane_stride; // elements between planes
+    size_t m, n;
+    int num_moduli;
+    void *C;
+    size_t ldc;
+    const int16_t *sftA, *sftB;
+    const void *alpha, *beta; // host or device pointers (resolved by the launcher)
+};
+int launch_crt(const CrtArgs &c, int dtype, cudaStream_t st);
+
+} // namespace g8

@@ -1,0 +1,111 @@
+/*
+ * gemmul8_b200 -- thin C ABI of the B200-native Ozaki-II GEMM emulator (the drop-in boundary).
+ *
+ * Plain pointers and sizes only: this is what a foreign-function binding (ctypes, cgo, JNI ...) or the
+ * C++ shims in include/gemmul8.hpp bind.  Every entry point cites the reference interface it replaces
+ * (paths relative to the reference tree RIKEN-RCCS/GEMMul8 @ 71296f9, GEMMul8/...).
+ *
+ * All matrix / workspace pointers are DEVICE pointers; alpha / beta may be host or device pointers
+ * (detected at run time exactly as reference src/inverse_scaling_real.hpp:211-213 does).  Column-major
+ * BLAS conventions.  Work is enqueued on `stream`; nothing blocks the host unless timing is requested.
+ *
+ * Return value: 0 on success, otherwise a G8_STATUS_* / cudaError_t-compatible positive code.  The
+ * reference's own API cannot report errors (it returns a timing vector and ignores CUDA status,
+ * src/matmult.hpp:136-143); the C++ shims therefore drop the code, the C ABI exposes it.
+ */
+#ifndef GEMMUL8_C_H
+#define GEMMUL8_C_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* gemmul8::Backend (include/gemmul8.hpp:19-20) */
+enum { G8_BACKEND_INT8 = 0, G8_BACKEND_FP8 = 1 };
+/* T of gemmul8::gemm<T,...> (src/gemmul8.cu:115-157) */
+enum { G8_R32F = 0, G8_R64F = 1, G8_C32F = 2, G8_C64F = 3 };
+/* cublasOperation_t values */
+enum { G8_OP_N = 0, G8_OP_T = 1, G8_OP_C = 2 };
+
+enum {
+    G8_STATUS_SUCCESS        = 0,
+    G8_STATUS_INVALID_VALUE  = 10001, /* bad enum / null pointer / num_moduli out of [2,20] (FP64) or [2,13] (FP32) / k > 2^17 */
+    G8_STATUS_NOT_SUPPORTED  = 10002, /* backend or shape this build does not implement (e.g. FP8 backend) */
+    G8_STATUS_NO_DEVICE_CODE = 10003  /* the sm_100a kernels cannot run on this device: there is NO fallback path */
+};
+
+/* gemmul8::workSize<is_Complex, backend>  (include/gemmul8.hpp:25-35, src/gemmul8_real.hpp:9-47,
+ * src/gemmul8_complex.hpp:9-47).  Same byte counts as the reference so caller-sized buffers keep working. */
+size_t g8_work_size(int is_complex, int backend, size_t m, size_t n, size_t k, unsigned num_moduli,
+                    int enable_skip_scalA, int enable_skip_scalB, size_t *workSizeA, size_t *workSizeB);
+
+/* Argument block of one emulated GEMM: field for field the parameter list of gemmul8::gemm / gemmLt
+ * (include/gemmul8.hpp:41-94); `stream` is the cudaStream_t (gemmLt's last argument, or the handle's
+ * stream for gemm, src/gemmul8.cu:116-118). */
+typedef struct g8_gemm_desc {
+    int dtype;   /* G8_R32F .. G8_C64F */
+    int backend; /* G8_BACKEND_* */
+    int op_A, op_B;
+    size_t m, n, k;
+    const void *alpha;
+    const void *A;
+    size_t lda;
+    const void *B;
+    size_t ldb;
+    const void *beta;
+    void *C;
+    size_t ldc;
+    unsigned num_moduli;
+    int fastmode;
+    void *work, *workA, *workB;
+    int enable_skip_scalA, enable_skip_scalB, skip_scalA, skip_scalB;
+    void *stream;
+} g8_gemm_desc;
+
+/* gemmul8::gemm<T,backend> / gemmul8::gemmLt<T,backend>  (src/gemmul8.cu:115-157 -> real::gemm
+ * src/gemmul8_real.hpp:53-211, complex::gemm src/gemmul8_complex.hpp:53-226).
+ * phase_ns: optional double[4] {split, gemm, requant(=0: fused), crt} in nanoseconds, measured with CUDA
+ * events; passing non-NULL makes the call synchronise the stream at the end (the reference always does,
+ * src/common.hpp:44-57).  NULL keeps the call fully asynchronous. */
+int g8_gemm(const g8_gemm_desc *d, double *phase_ns);
+
+/* ---- stage-level entry points (used by the K-sharded multi-GPU driver and by the parity tests) ---- */
+
+/* Stage 1 for ONE operand with externally supplied shifts: planes <- trunc(op(X) * 2^-sft) mod p_i.
+ * is_A selects the m x k (A) or k x n (B) role.  Replaces scalingA/B kernels (src/scaling_fast_real.hpp:54-164). */
+int g8_stage_split(int dtype, int is_A, int op, size_t rows, size_t k, const void *X, size_t ld, unsigned num_moduli,
+                   int mode /*0: use sft, 1: fast (computes sft), 2: accurate bound plane + s0*/, int16_t *sft,
+                   int8_t *planes, size_t plane_stride_bytes, size_t group_stride_planes, void *stream);
+
+/* accurate mode stage (iii): sft[i] = -(s0[i] + floor(log2P - 0.5000001*log2(cmax[i])))  (src/scaling_accu_real.hpp:6-11,157-159) */
+int g8_stage_finalize_shift(int16_t *sft, const int32_t *cmax, size_t count, unsigned num_moduli, void *stream);
+
+/* Stage 2: the low-precision GEMMs over planes (src/matmult.hpp:120-302 + src/conv_hi2mid_*.hpp).
+ * epilogue: 0 mod-p int8, 1 raw int32, 2 row/col max (bound GEMM), 3 complex mod-p, 4 complex bound max.
+ * use_simt != 0 selects the slow dp4a cross-check kernel (tests only). */
+int g8_stage_gemm(int epilogue, int use_simt, const int8_t *A_lo, size_t strideA, const int8_t *B_lo, size_t strideB, size_t m,
+                  size_t n, size_t k_pad, int num_units, int first_modulus, const int *groupA, const int *groupB, void *out,
+                  size_t out_stride, size_t ldc, int32_t *rowmax, int32_t *colmax, void *stream);
+
+/* Stage 3: CRT accumulate + unscale + alpha/beta (src/inverse_scaling_real.hpp:242-278, _complex.hpp:286-326) */
+int g8_stage_crt(int dtype, const void *C_mid, size_t ldmid, size_t plane_stride, size_t m, size_t n, unsigned num_moduli, void *C,
+                 size_t ldc, const int16_t *sftA, const int16_t *sftB, const void *alpha, const void *beta, void *stream);
+
+/* C_mid[i] = sym(C_hi[i] mod p_i) for int32 planes that were summed across K-shards (src/conv_hi2mid_real.hpp:9-25) */
+int g8_stage_requant_i32(const int32_t *C_hi, size_t count_per_plane, int num_units, int first_modulus, int8_t *C_mid, void *stream);
+
+/* Synthetic test matrices with the reference harness' generator (testing/make_matrix.hpp:33-82):
+ * element idx <- curand_init(seed, idx, 0); phi < 0: standard normal, else (u-0.5)*exp(g*phi). */
+int g8_randmat(int dtype, void *X, size_t rows, size_t cols, double phi, unsigned long long seed, void *stream);
+
+/* build / device introspection */
+const char *g8_version(void);
+int g8_device_supported(int device); /* 1 iff compute capability 10.0 (sm_100a cubin loads) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEMMUL8_C_H */

@@ -1,0 +1,312 @@
+#!/usr/bin/env python3
+"""Stage-by-stage bring-up checks on a real B200 (run under gpurun; each stage is meant to be wrapped in
+`timeout` so that a hung kernel cannot stall the box):
+
+    python tools/gpu_debug.py split|simt|crt|tc|e2e|ref|all
+
+Every check compares against oracle/ (the CPU restatement) or, for `ref`, the unmodified reference
+library in oracle/_ref.  This is test infrastructure, not product code."""
+import ctypes
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import gemmul8_b200 as g8  # noqa: E402
+from gemmul8_b200 import _lib, api, tables as T  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+import helpers as H  # noqa: E402
+
+lib = _lib.load()
+rng = np.random.default_rng(1234)
+FAILS = []
+
+
+def report(name, ok, extra=""):
+    print(("PASS " if ok else "FAIL ") + name + (" " + extra if extra else ""), flush=True)
+    if not ok:
+        FAILS.append(name)
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def stage_split(dtype=np.float64, rows=70, k=300, N=14, op="N", is_A=True, mode=0, sft=None):
+    """returns planes [G][N, rows, k_pad], sft (device result)"""
+    shape = H.stored_shape(op, rows, k) if is_A else H.stored_shape(op, k, rows)
+    X = H.rand_matrix(rng, shape, dtype)
+    dX, ld = H.to_dev_colmajor(X)
+    k_pad = api.pad256(k)
+    cplx = np.dtype(dtype).kind == "c"
+    G = 3 if cplx else 1
+    planes = torch.full((G, N, rows, k_pad), 77, dtype=torch.int8, device="cuda")
+    dsft = torch.zeros(api.pad256(rows), dtype=torch.int16, device="cuda")
+    if sft is not None:
+        dsft[:rows] = torch.from_numpy(sft).cuda()
+    dt = api._DTYPES[H.NP2T[np.dtype(dtype)]]
+    code = lib.g8_stage_split(dt, int(is_A), api._op(op), rows, k, dX.data_ptr(), ld, N, mode, dsft.data_ptr(),
+                              planes.data_ptr(), rows * k_pad, N, stream())
+    torch.cuda.synchronize()
+    assert code == 0, code
+    return X, planes.cpu().numpy(), dsft[:rows].cpu().numpy()
+
+
+def check_split():
+    for dtype in (np.float64, np.float32, np.complex128, np.complex64):
+        for N in (6, 14, 18):
+            if np.dtype(dtype) in (np.dtype(np.float32), np.dtype(np.complex64)) and N > 13:
+                continue
+            for is_A in (True, False):
+                for op in ("N", "T", "C"):
+                    rows, k = 70, 300
+                    # fast mode: device computes sft; oracle splits with the device shifts
+                    X, planes, sft = stage_split(dtype, rows, k, N, op, is_A, mode=1)
+                    oper = O.Operand(X, op, is_A)
+                    ref = O.split(oper, sft, N)
+                    ok = all(np.array_equal(planes[g], ref[g]) for g in range(len(ref)))
+                    # shift sanity vs CPU formula
+                    dummy = O.Operand(np.zeros((1, 1), dtype=dtype), "N", not is_A)
+                    sA, _, amb, _ = O.fast_shifts(oper, oper, N)
+                    bad = np.sum((sA != sft) & ~amb)
+                    report(f"split fast {np.dtype(dtype).name} N={N} {'A' if is_A else 'B'} op={op}", ok and bad == 0,
+                           "" if ok else H.first_diff(planes[0], ref[0], "plane") + f" sft_bad={bad} dev={sft[:4]} cpu={sA[:4]}")
+                    if not ok or bad:
+                        print("   sft dev", sft[:8], "cpu", sA[:8])
+
+
+def rand_planes(N, rows, k_pad, k, lo=-127, hi=127):
+    P = rng.integers(lo, hi + 1, size=(N, rows, k_pad), dtype=np.int64).astype(np.int8)
+    P[:, :, k:] = 0
+    return P
+
+
+def run_stage_gemm(epi, use_simt, A_lo, B_lo, m, n, N, groups=None, cplx=False):
+    """A_lo: np int8 [planes, m_pad_or_m, k_pad]; returns output array"""
+    k_pad = A_lo.shape[-1]
+    m_pad = api.pad256(m)
+    dA = torch.from_numpy(A_lo).cuda()
+    dB = torch.from_numpy(B_lo).cuda()
+    strideA = A_lo.shape[1] * k_pad
+    strideB = B_lo.shape[1] * k_pad
+    ga = (ctypes.c_int * 3)(*(groups or (0, 0, 0)))
+    gb = (ctypes.c_int * 3)(*(groups or (0, 0, 0)))
+    rowmax = torch.zeros(m_pad, dtype=torch.int32, device="cuda")
+    colmax = torch.zeros(api.pad256(n), dtype=torch.int32, device="cuda")
+    if epi == 0:
+        out = torch.full((N, n, m_pad), 99, dtype=torch.int8, device="cuda")
+    elif epi == 1:
+        out = torch.full((N, n, m_pad), 99, dtype=torch.int32, device="cuda")
+    elif epi == 3:
+        out = torch.full((N, n, m_pad, 2), 99, dtype=torch.int8, device="cuda")
+    else:
+        out = torch.zeros(1, dtype=torch.int8, device="cuda")
+    code = lib.g8_stage_gemm(epi, int(use_simt), dA.data_ptr(), strideA, dB.data_ptr(), strideB, m, n, k_pad, N, 0, ga, gb,
+                             out.data_ptr(), m_pad * n, m_pad, rowmax.data_ptr(), colmax.data_ptr(), stream())
+    torch.cuda.synchronize()
+    assert code == 0, code
+    return out.cpu().numpy(), rowmax.cpu().numpy(), colmax.cpu().numpy()
+
+
+def ref_cmid(A_lo, B_lo, m, n, N):
+    mod = T.moduli("INT8")
+    out = np.zeros((N, n, api.pad256(m)), dtype=np.int8)
+    for i in range(N):
+        H32 = A_lo[i, :m].astype(np.int64) @ B_lo[i].astype(np.int64).T  # m x n
+        p = mod[i]
+        r = np.mod(H32, p)
+        r = np.where(r > p // 2, r - p, r)
+        out[i, :, :m] = r.T.astype(np.int8)
+    return out
+
+
+def check_gemm(use_simt, shapes):
+    tag = "simt" if use_simt else "tc"
+    for (m, n, k, N) in shapes:
+        k_pad = api.pad256(k)
+        A_lo = rand_planes(N, m, k_pad, k, -128, 127)
+        B_lo = rand_planes(N, n, k_pad, k, -128, 127)
+        t0 = time.time()
+        out, _, _ = run_stage_gemm(0, use_simt, A_lo, B_lo, m, n, N)
+        dt = time.time() - t0
+        ref = ref_cmid(A_lo, B_lo, m, n, N)
+        ok = np.array_equal(out[:, :, :m], ref[:, :, :m])
+        report(f"gemm {tag} mod m={m} n={n} k={k} N={N}", ok, f"({dt:.2f}s) " + ("" if ok else H.first_diff(out[:, :, :m], ref[:, :, :m], "C_mid")))
+        if not ok:
+            d = np.argwhere(out[:, :, :m] != ref[:, :, :m])
+            print("   diff units:", np.unique(d[:, 0])[:10], "cols:", np.unique(d[:, 1])[:10], "rows:", np.unique(d[:, 2])[:10], flush=True)
+        # raw int32
+        out32, _, _ = run_stage_gemm(1, use_simt, A_lo[:2], B_lo[:2], m, n, 2)
+        ref32 = np.stack([(A_lo[i, :m].astype(np.int64) @ B_lo[i].astype(np.int64).T).T for i in range(2)]).astype(np.int32)
+        ok = np.array_equal(out32[:, :, :m], ref32)
+        report(f"gemm {tag} raw32 m={m} n={n} k={k}", ok, "" if ok else H.first_diff(out32[:, :, :m], ref32, "C_hi"))
+        # bound max (non-negative operands)
+        Ab = rand_planes(1, m, k_pad, k, 0, 64)
+        Bb = rand_planes(1, n, k_pad, k, 0, 64)
+        _, rmax, cmax = run_stage_gemm(2, use_simt, Ab, Bb, m, n, 1)
+        Cb = Ab[0, :m].astype(np.int64) @ Bb[0].astype(np.int64).T
+        ok = np.array_equal(rmax[:m], Cb.max(axis=1)) and np.array_equal(cmax[:n], Cb.max(axis=0))
+        report(f"gemm {tag} boundmax m={m} n={n} k={k}", ok)
+        # complex 3M
+        Nc = min(N, 3)
+        Ar, Ai = rand_planes(Nc, m, k_pad, k), rand_planes(Nc, m, k_pad, k)
+        Br, Bi = rand_planes(Nc, n, k_pad, k), rand_planes(Nc, n, k_pad, k)
+        mod = T.moduli("INT8")
+
+        def ri(x, y):
+            s = x.astype(np.int32) + y.astype(np.int32)
+            o = np.empty_like(x)
+            for i in range(Nc):
+                p = mod[i]
+                o[i] = np.where(s[i] > p // 2, s[i] - p, np.where(s[i] < -(p // 2), s[i] + p, s[i])).astype(np.int8)
+            return o
+        A3 = np.concatenate([Ar, Ai, ri(Ar, Ai)])
+        B3 = np.concatenate([Br, Bi, ri(Br, Bi)])
+        outc, _, _ = run_stage_gemm(3, use_simt, A3, B3, m, n, Nc, groups=(0, Nc, 2 * Nc))
+        refc = np.zeros((Nc, n, api.pad256(m), 2), dtype=np.int8)
+        for i in range(Nc):
+            p = mod[i]
+            ar, ai, br, bi = (x[i].astype(np.int64) for x in (Ar[:, :m], Ai[:, :m], Br, Bi))
+            re = ar @ br.T - ai @ bi.T
+            im = ar @ bi.T + ai @ br.T
+            for j, v in enumerate((re, im)):
+                r = np.mod(v, p)
+                r = np.where(r > p // 2, r - p, r)
+                refc[i, :, :m, j] = r.T.astype(np.int8)
+        ok = np.array_equal(outc[:, :, :m], refc[:, :, :m])
+        report(f"gemm {tag} cplx3m m={m} n={n} k={k}", ok, "" if ok else H.first_diff(outc[:, :, :m], refc[:, :, :m], "C_mid"))
+        # complex bound
+        _, rmax, cmax = run_stage_gemm(4, use_simt, np.concatenate([Ab, Ab[:, ::-1]]), np.concatenate([Bb, Bb[:, ::-1]]), m, n, 1,
+                                       groups=(0, 1, 2))
+        a0, a1 = Ab[0, :m].astype(np.int64), Ab[0, ::-1][:m].astype(np.int64)
+        b0, b1 = Bb[0].astype(np.int64), Bb[0, ::-1].astype(np.int64)
+        Cm = np.maximum(a0 @ b0.T + a1 @ b1.T, a0 @ b1.T + a1 @ b0.T)
+        ok = np.array_equal(rmax[:m], Cm.max(axis=1)) and np.array_equal(cmax[:n], Cm.max(axis=0))
+        report(f"gemm {tag} cplxbound m={m} n={n} k={k}", ok)
+
+
+def check_crt():
+    for dtype in (np.float64, np.float32, np.complex128, np.complex64):
+        for N in (2, 6, 7, 14, 20):
+            m, n = 67, 9
+            m_pad = api.pad256(m)
+            cplx = np.dtype(dtype).kind == "c"
+            shape = (N, n, m_pad, 2) if cplx else (N, n, m_pad)
+            Cmid = rng.integers(-127, 128, size=shape).astype(np.int8)
+            for i, p in enumerate(T.moduli("INT8")[:N]):
+                Cmid[i] = np.clip(Cmid[i], -(p // 2), p // 2)
+            sA = rng.integers(-60, -20, size=m).astype(np.int16)
+            sB = rng.integers(-60, -20, size=n).astype(np.int16)
+            C0 = H.rand_matrix(rng, (m, n), dtype)
+            for (alpha, beta, dev) in ((1, 0, False), (1, 1, False), (-1, 0, False), (-1, 1, False), (0.75, -1.5, False), (0.75, -1.5, True), (1, 0, True)):
+                if cplx and alpha == 0.75:
+                    alpha, beta = 0.75 - 0.5j, -1.5 + 0.25j
+                ref = O.crt(Cmid, m, n, N, sA, sB, dtype, alpha, beta, C0, device_scalars=dev)
+                dC, ldc = H.to_dev_colmajor(C0)
+                dmid = torch.from_numpy(Cmid).cuda()
+                dsA = torch.zeros(m_pad, dtype=torch.int16, device="cuda"); dsA[:m] = torch.from_numpy(sA).cuda()
+                dsB = torch.zeros(api.pad256(n), dtype=torch.int16, device="cuda"); dsB[:n] = torch.from_numpy(sB).cuda()
+                keep = []
+                tdt = H.NP2T[np.dtype(dtype)]
+                if dev:
+                    a_t = torch.tensor([alpha], dtype=tdt, device="cuda"); b_t = torch.tensor([beta], dtype=tdt, device="cuda")
+                    pa, pb = a_t.data_ptr(), b_t.data_ptr()
+                else:
+                    pa, pb = api._scalar_ptr(alpha, tdt, keep), api._scalar_ptr(beta, tdt, keep)
+                code = lib.g8_stage_crt(api._DTYPES[tdt], dmid.data_ptr(), m_pad, m_pad * n, m, n, N, dC.data_ptr(), ldc,
+                                        dsA.data_ptr(), dsB.data_ptr(), pa, pb, stream())
+                torch.cuda.synchronize()
+                out = H.from_dev_colmajor(dC, m, n, ldc)
+                ok = code == 0 and H.bits_equal(out, ref)
+                report(f"crt {np.dtype(dtype).name} N={N} a={alpha} b={beta} dev={dev}", ok, "" if ok else H.first_diff(out, ref, "C"))
+
+
+def check_e2e():
+    kat = __import__("json").load(open(ROOT / "tests/golden/sample_kat.json"))
+    A = np.array([float.fromhex(x) for x in kat["A"]]).reshape(5, 4).T
+    B = np.array([float.fromhex(x) for x in kat["B"]]).reshape(3, 5).T
+    Cx = np.array([float.fromhex(x) for x in kat["C_exact"]]).reshape(3, 4).T
+    C = H.run_gemm(A, B, num_moduli=15, fastmode=False)
+    report("e2e KAT sample N=15 accurate", H.bits_equal(C, Cx), f"err={np.linalg.norm(C - Cx):.3e}")
+    for dtype, N in ((np.float64, 14), (np.float32, 6), (np.complex128, 18), (np.complex64, 6), (np.float64, 18), (np.float64, 7)):
+        for fast in (False, True):
+            for opA, opB in (("N", "N"), ("T", "N"), ("N", "T"), ("C", "C")):
+                m, n, k = 150, 70, 333
+                A = H.rand_matrix(rng, H.stored_shape(opA, m, k), dtype)
+                B = H.rand_matrix(rng, H.stored_shape(opB, k, n), dtype)
+                C, W = H.run_gemm(A, B, opA, opB, N, fast, return_work=True)
+                r = O.emulate(A, B, opA, opB, N, fast, sftA=W["sftA"], sftB=W["sftB"])
+                okp = all(np.array_equal(W["A_lo"][g], r["A_lo"][g]) for g in range(len(r["A_lo"]))) and \
+                    all(np.array_equal(W["B_lo"][g], r["B_lo"][g]) for g in range(len(r["B_lo"])))
+                okm = np.array_equal(W["C_mid"][:, :, :m], r["C_mid"][:, :, :m])
+                okc = H.bits_equal(C, r["C"])
+                r2 = O.emulate(A, B, opA, opB, N, fast)
+                badA = int(np.sum((r2["sftA"] != W["sftA"]) & ~r2["ambA"]))
+                badB = int(np.sum((r2["sftB"] != W["sftB"]) & ~r2["ambB"]))
+                opx = {"N": A, "T": A.T, "C": A.conj().T}[opA] @ {"N": B, "T": B.T, "C": B.conj().T}[opB]
+                err = np.abs(C - opx).max() / np.abs(opx).max()
+                report(f"e2e {np.dtype(dtype).name} N={N} fast={fast} {opA}{opB}", okp and okm and okc and badA == 0 and badB == 0,
+                       f"planes={okp} cmid={okm} C={okc} sftbad=({badA},{badB}) relerr={err:.2e}")
+
+
+def check_ref():
+    so = ROOT / "oracle/_ref/libgemmul8_ref.so"
+    R = ctypes.CDLL(str(so))
+    R.ref_work_size.restype = ctypes.c_size_t
+    R.ref_work_size.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_size_t] * 3 + [ctypes.c_uint, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    R.ref_gemm.restype = ctypes.c_int
+    R.ref_gemm.argtypes = [ctypes.c_int] * 5 + [ctypes.c_size_t] * 3 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                           ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint, ctypes.c_int] + \
+        [ctypes.c_void_p] * 3 + [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p]
+    for dtype, N, (m, n, k) in ((np.float64, 14, (300, 200, 1000)), (np.float32, 6, (257, 129, 515)), (np.complex128, 18, (130, 90, 400)),
+                                (np.complex64, 6, (130, 90, 400)), (np.float64, 20, (64, 64, 256)), (np.float64, 14, (1024, 1024, 1024))):
+        for fast in (False, True):
+            for opA, opB in (("N", "N"), ("T", "T")):
+                A = H.rand_matrix(rng, H.stored_shape(opA, m, k), dtype, phi=1.0)
+                B = H.rand_matrix(rng, H.stored_shape(opB, k, n), dtype, phi=1.0)
+                C, W = H.run_gemm(A, B, opA, opB, N, fast, return_work=True)
+                cplx = np.dtype(dtype).kind == "c"
+                dA, lda = H.to_dev_colmajor(A); dB, ldb = H.to_dev_colmajor(B)
+                dC, ldc = H.to_dev_colmajor(np.zeros((m, n), dtype=dtype))
+                tot = R.ref_work_size(int(cplx), 0, m, n, k, N, 0, 0, None, None)
+                work = torch.zeros(tot, dtype=torch.uint8, device="cuda")
+                keep = []
+                tdt = H.NP2T[np.dtype(dtype)]
+                pa, pb = api._scalar_ptr(1.0, tdt, keep), api._scalar_ptr(0.0, tdt, keep)
+                timing = (ctypes.c_double * 4)()
+                code = R.ref_gemm(api._DTYPES[tdt], 0, 1, api._op(opA), api._op(opB), m, n, k, pa, dA.data_ptr(), lda, dB.data_ptr(), ldb,
+                                  pb, dC.data_ptr(), ldc, N, int(fast), work.data_ptr(), None, None, 0, 0, 0, 0,
+                                  ctypes.c_void_p(stream()), timing)
+                torch.cuda.synchronize()
+                Cr = H.from_dev_colmajor(dC, m, n, ldc)
+                Wr = H.read_workspace(work, m, n, k, N, cplx)
+                oks = np.array_equal(W["sftA"], Wr["sftA"]) and np.array_equal(W["sftB"], Wr["sftB"])
+                okm = np.array_equal(W["C_mid"][:, :, :m], Wr["C_mid"][:, :, :m])
+                okc = H.bits_equal(C, Cr)
+                report(f"ref-parity {np.dtype(dtype).name} N={N} {m}x{n}x{k} fast={fast} {opA}{opB}", code == 0 and oks and okm and okc,
+                       f"sft={oks} cmid={okm} C={okc}" + ("" if oks else f" sftA dev{W['sftA'][:6]} ref{Wr['sftA'][:6]} ndiffA={np.sum(W['sftA']!=Wr['sftA'])} ndiffB={np.sum(W['sftB']!=Wr['sftB'])}"))
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    print("device:", torch.cuda.get_device_name(0), lib.g8_version().decode(), flush=True)
+    if what in ("split", "all"):
+        check_split()
+    if what in ("simt", "all"):
+        check_gemm(True, [(70, 50, 300, 3), (130, 257, 256, 4)])
+    if what in ("crt", "all"):
+        check_crt()
+    if what in ("tc", "all"):
+        check_gemm(False, [(128, 128, 256, 2), (70, 50, 300, 3), (300, 200, 1000, 14), (512, 384, 2048, 4)])
+    if what in ("e2e", "all"):
+        check_e2e()
+    if what in ("ref", "all"):
+        check_ref()
+    print("FAILED:" if FAILS else "ALL PASSED", FAILS[:20], flush=True)
+    sys.exit(1 if FAILS else 0)
