@@ -1,0 +1,63 @@
+"""The C-ABI library loads on a machine WITHOUT a GPU and exports every symbol include/gemmul8_c.h declares;
+host-only entry points behave like the reference (workSize golden values from the reference library)."""
+import ctypes
+import json
+import re
+from pathlib import Path
+
+import pytest
+
+from gemmul8_b200 import _lib
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols():
+    hdr = (ROOT / "include/gemmul8_c.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(g8_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_all_exported_and_bound():
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/gemmul8_c.h but not exported by libg8core.so"
+    assert set(names) == set(_lib.SYMBOLS), "python binding table out of sync with the header"
+
+
+def test_version_string():
+    assert b"sm_100a" in _lib.load().g8_version()
+
+
+def test_work_size_matches_reference_golden():
+    import gemmul8_b200 as g8
+
+    gold = json.loads((ROOT / "tests/golden/worksize.json").read_text())["rows"]
+    for cplx, be, m, n, k, N, ea, eb, tot, wa, wb in gold:
+        assert g8.work_size(m, n, k, N, bool(cplx), be, bool(ea), bool(eb)) == (tot, wa, wb), (cplx, be, m, n, k, N, ea, eb)
+
+
+def test_compute_entry_points_fail_loudly_without_gpu():
+    """No CPU fallback: without a CUDA device the compute calls return an error code, never a result."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.load()
+    d = _lib.GemmDesc()
+    d.dtype, d.backend, d.m, d.n, d.k, d.num_moduli = 1, 0, 4, 4, 4, 14
+    buf = (ctypes.c_double * 64)()
+    p = ctypes.addressof(buf)
+    d.A = d.B = d.C = d.alpha = d.beta = d.work = p
+    assert lib.g8_gemm(ctypes.byref(d), None) != 0
+    d.num_moduli = 1
+    assert lib.g8_gemm(ctypes.byref(d), None) == 10001  # INVALID_VALUE before touching the device
+
+
+def test_native_library_missing_is_an_error(monkeypatch, tmp_path):
+    monkeypatch.setenv("GEMMUL8_B200_LIB", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(_lib, "_lib", None)
+    with pytest.raises(_lib.NativeLibraryMissing):
+        _lib.load()
