@@ -7,21 +7,26 @@
 //   hi/lo chain (T double, N > P_is_double):      H = fma(w_i.x, c_i, H); L = fma(w_i.y, c_i, L);
 //                                                 q = rint(invP*H); r = fma(P.y, q, fma(P.x, q, H) + L)
 //   AB = scalbn((T)r, sftA[row] + sftB[col]);  then C = AB | C+AB | -AB | C-AB | fma(beta, C, alpha*AB).
-// What changes is the memory access: each thread owns 16 bytes of output (2 doubles / 4 floats / 1 double2 /
-// 2 float2) of one column, so plane loads are contiguous per warp and stores are full 128-bit coalesced,
-// instead of one element per thread with N strided byte loads.
+// What changes is the memory access and the instruction mix: each thread owns 8 consecutive residues of one column
+// (one 64-bit load per plane, 128-bit stores), and int8 -> double goes through a mantissa splice + one DADD
+// instead of I2F.F64 (quarter-rate pipe), instead of one element per thread with N strided byte loads.
 #include "g8_internal.cuh"
 
 namespace g8 {
 
 template <typename T> struct CrtTraits;
-template <> struct CrtTraits<float>   { using U = float;  static constexpr bool cplx = false; static constexpr int VEC = 4; };
-template <> struct CrtTraits<double>  { using U = double; static constexpr bool cplx = false; static constexpr int VEC = 2; };
-template <> struct CrtTraits<float2>  { using U = float;  static constexpr bool cplx = true;  static constexpr int VEC = 2; };
-template <> struct CrtTraits<double2> { using U = double; static constexpr bool cplx = true;  static constexpr int VEC = 1; };
+template <> struct CrtTraits<float>   { using U = float;  static constexpr bool cplx = false; };
+template <> struct CrtTraits<double>  { using U = double; static constexpr bool cplx = false; };
+template <> struct CrtTraits<float2>  { using U = float;  static constexpr bool cplx = true;  };
+template <> struct CrtTraits<double2> { using U = double; static constexpr bool cplx = true;  };
 
+// v * 2^s.  The reference calls scalbn()/scalbnf(); CUDA's scalbn is a single multiplication by the exactly
+// representable 2^s whenever |s| <= 1021, which we issue directly (bit-identical); otherwise defer to the library.
+__device__ __forceinline__ double scal(double v, int s) {
+    if (abs(s) <= 1021) return __dmul_rn(v, __longlong_as_double((long long)(1023 + s) << 52));
+    return scalbn(v, s);
+}
 __device__ __forceinline__ float  scal(float v, int s) { return scalbnf(v, s); }
-__device__ __forceinline__ double scal(double v, int s) { return scalbn(v, s); }
 __device__ __forceinline__ float  fma_(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
 
@@ -29,43 +34,51 @@ struct Scalars {
     double ar, ai, br, bi; // host scalars widened (exact); used in MODE 4
 };
 
+constexpr int CRT_NV = 4; // residue bytes (= scalar outputs) per thread: one 32-bit load per plane (128 B per warp);
+                          // small per-thread state -> full occupancy hides the serial FMA chains
+
 // MODE: 0 C=AB, 1 C+=AB, 2 C=-AB, 3 C-=AB, 4 general (host scalars), 5 general (device scalars)
 template <typename T, bool DD, int MODE, bool VECIO>
 __global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t groups, size_t total) {
     using TR           = CrtTraits<T>;
     using U            = typename TR::U;
-    constexpr int VEC  = TR::VEC;
-    constexpr int NV   = TR::cplx ? 2 * VEC : VEC; // scalar lanes per thread (always 16 bytes of output... or 4/2)
+    constexpr int NV   = CRT_NV;
+    constexpr int VEC  = TR::cplx ? NV / 2 : NV; // rows per thread
     const size_t idx   = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const size_t col = idx / groups;
     const size_t row = (idx - col * groups) * VEC;
     const int N      = c.num_moduli;
 
-    // ---- accumulate over moduli (i ascending) ----
+    // ---- accumulate over moduli (i ascending).  int8 -> double without the slow I2F path: the byte c+128 is
+    //      spliced into the mantissa of 2^52 and (2^52 + 128) is subtracted (exact). ----
     double hi[NV], lo[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) hi[j] = 0.0, lo[j] = 0.0;
     const int8_t *src = reinterpret_cast<const int8_t *>(c.C_mid) + (col * c.ldmid + row) * (TR::cplx ? 2 : 1);
     const size_t pstride = c.plane_stride * (TR::cplx ? 2 : 1);
     const int tbl1 = N - 2, tbl2 = N - thresholds(INT8).P_is_double - 1;
-#pragma unroll 2
+    constexpr double kOff = 4503599627370496.0 + 128.0;
+#pragma unroll 4
     for (int i = 0; i < N; ++i) {
-        int8_t r[NV];
-        if constexpr (NV == 4) *reinterpret_cast<uint32_t *>(r) = *reinterpret_cast<const uint32_t *>(src + (size_t)i * pstride);
-        else *reinterpret_cast<uint16_t *>(r) = *reinterpret_cast<const uint16_t *>(src + (size_t)i * pstride);
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)i * pstride)) ^ 0x80808080u;
+        double cd[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const uint32_t b = __byte_perm(w, 0u, 0x4440 + j);
+            cd[j]            = __dadd_rn(__hiloint2double(0x43300000, (int)b), -kOff);
+        }
         if constexpr (DD) {
             const double wx = g8d_qPi2[INT8][tbl2][i][0], wy = g8d_qPi2[INT8][tbl2][i][1];
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
-                const double cd = (double)r[j];
-                hi[j]           = fma(wx, cd, hi[j]);
-                lo[j]           = fma(wy, cd, lo[j]);
+                hi[j] = fma(wx, cd[j], hi[j]);
+                lo[j] = fma(wy, cd[j], lo[j]);
             }
         } else {
-            const double w = g8d_qPi1[INT8][tbl1][i];
+            const double wv = g8d_qPi1[INT8][tbl1][i];
 #pragma unroll
-            for (int j = 0; j < NV; ++j) hi[j] = fma(w, (double)r[j], hi[j]);
+            for (int j = 0; j < NV; ++j) hi[j] = fma(wv, cd[j], hi[j]);
         }
     }
 
@@ -73,11 +86,14 @@ __global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t 
     const double invP = g8d_invP[INT8][N - 2];
     const double Px = g8d_P[INT8][N - 2][0], Py = g8d_P[INT8][N - 2][1];
     const int sB = c.sftB[col];
+    // sftA has pad256(m) entries, so the (unused) tail rows of the last group may be read safely; row % VEC == 0
+    int16_t sA[VEC];
+    if constexpr (VEC == 4) *reinterpret_cast<uint2 *>(sA) = *reinterpret_cast<const uint2 *>(c.sftA + row);
+    else *reinterpret_cast<uint32_t *>(sA) = *reinterpret_cast<const uint32_t *>(c.sftA + row);
     U ab[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-        const size_t rj = row + (TR::cplx ? j / 2 : j);
-        const int sft   = (rj < c.m ? (int)c.sftA[rj] : 0) + sB;
+        const int sft   = (int)sA[TR::cplx ? j / 2 : j] + sB;
         const double q  = rint(invP * hi[j]);
         double r;
         if constexpr (DD) r = fma(Py, q, fma(Px, q, hi[j]) + lo[j]);
@@ -88,10 +104,13 @@ __global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t 
     // ---- alpha / beta ----
     U *dst = reinterpret_cast<U *>(c.C) + (col * c.ldc + row) * (TR::cplx ? 2 : 1);
     const int valid = (int)min((size_t)VEC, c.m - row) * (TR::cplx ? 2 : 1);
+    constexpr int PER16 = 16 / sizeof(U); // scalars per 128-bit access
+    const bool full = VECIO && valid == NV;
     U old[NV];
     if constexpr (MODE == 1 || MODE == 3 || MODE >= 4) {
-        if (VECIO && valid == NV) {
-            *reinterpret_cast<uint4 *>(old) = *reinterpret_cast<const uint4 *>(dst);
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < NV; j += PER16) *reinterpret_cast<uint4 *>(old + j) = *reinterpret_cast<const uint4 *>(dst + j);
         } else {
 #pragma unroll
             for (int j = 0; j < NV; ++j) old[j] = (j < valid) ? dst[j] : U(0);
@@ -132,8 +151,9 @@ __global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t 
             for (int j = 0; j < NV; ++j) out[j] = fma_(br, old[j], ar * ab[j]);
         }
     }
-    if (VECIO && valid == NV) {
-        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(out);
+    if (full) {
+#pragma unroll
+        for (int j = 0; j < NV; j += PER16) *reinterpret_cast<uint4 *>(dst + j) = *reinterpret_cast<const uint4 *>(out + j);
     } else {
 #pragma unroll
         for (int j = 0; j < NV; ++j)
@@ -142,7 +162,7 @@ __global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t 
 }
 
 template <typename T, bool DD, int MODE> static void crt_go(const CrtArgs &c, const Scalars &hs, cudaStream_t st) {
-    constexpr int VEC   = CrtTraits<T>::VEC;
+    constexpr int VEC   = CrtTraits<T>::cplx ? CRT_NV / 2 : CRT_NV;
     const size_t groups = (c.m + VEC - 1) / VEC;
     const size_t total  = groups * c.n;
     if (total == 0) return;

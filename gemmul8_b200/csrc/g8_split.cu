@@ -9,7 +9,7 @@
 //   row-strided    : rows are interleaved, element (r,l) at X[l*ld + r]      (A with op N, B with op T/C)
 // The row-contiguous kernels use one 256-thread block per row; the row-strided kernels transpose
 // 32 x 128 tiles through XOR-swizzled shared memory so that both the global loads (along r) and the
-// plane stores (16 B per lane, 128 B per row segment, along l) are fully coalesced.
+// plane stores (8 B per lane, 128 B per row segment, along l) are fully coalesced.
 //
 // Bit-parity notes.  The residues are the unique symmetric representatives, so any correct modular
 // arithmetic matches the reference.  The SHIFTS however depend on (a) MUFU.LG2 via __log2f and the
@@ -116,52 +116,165 @@ template <typename U> __device__ __forceinline__ int8_t upper_bound_i8(U a, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// scaled integer A' = trunc(a * 2^s) kept as (sign, 53-bit magnitude, left shift) and its residues.
-// REGIME 0: |A'| < 2^31 (N <= S), 1: |A'| < 2^63 (N <= M), 2: larger, shift > 10 possible (N > M).
+// Residues of the scaled integer x = trunc(a * 2^s) for all moduli.
+//
+// x is kept as a binary64 value (it is one: at most 53 significant bits).  Instead of the reference's
+// per-modulus 64-bit mulhi chains (mod.hpp:31-55) we reduce in two levels (gemmul8_b200/tables.py:fast_mod_tables):
+//   level 1 (FP64 pipe, once per group of three moduli):  r = x - M_g * rint(x / M_g), |r| <= 0.501 M_g < 2^24
+//   level 2 (integer pipes, per modulus):  a1 = int(r) + h + K p >= 0;  q = umulhi(a1, ceil(2^32/p)) = floor(a1/p) exactly;
+//                                          s = (a1 - h) - q p  in [-h, h]  -- the symmetric residue, no compare/select.
+// The results are the unique symmetric representatives, hence bit-identical to the reference's planes.
+// LARGE (num_moduli > 15): |x| may exceed 2^63, so level 1 first folds x modulo M_g * 2^20.
 // ------------------------------------------------------------------------------------------------
-struct Scaled {
-    int64_t v; // REGIME 0/1: the full signed value.  REGIME 2: signed 53-bit mantissa
-    int sh;    // REGIME 2 only: remaining left shift (>= 0)
-};
+constexpr double kMagic = 6755399441055744.0; // 1.5 * 2^52: (v + kMagic) - kMagic == rint(v) for |v| < 2^51
 
-template <int REGIME, typename U> __device__ __forceinline__ Scaled scale_trunc(U a_in, int s) {
-    const double a      = (double)a_in; // exact for float
-    const uint64_t raw  = (uint64_t)__double_as_longlong(a);
-    const int bexp      = (int)((raw >> 52) & 0x7FF);
-    const uint64_t frac = raw & 0xFFFFFFFFFFFFFull;
-    const uint64_t mant = bexp ? (frac | (1ull << 52)) : frac;
-    const int sh        = (bexp ? bexp - 1075 : -1074) + s;
-    Scaled r;
-    r.sh = 0;
-    uint64_t mag;
-    if (sh <= 0) {
-        mag = (sh > -64) ? (mant >> (-sh)) : 0ull;
-    } else if (REGIME < 2 || sh <= 10) {
-        mag = mant << (sh & 63);
-    } else {
-        mag  = mant;
-        r.sh = sh;
-    }
-    r.v = (raw >> 63) ? -(int64_t)mag : (int64_t)mag;
+struct RowScale {
+    double f1, f2; // 2^s split into two exactly representable factors (|s| may exceed 1023)
+};
+__device__ __forceinline__ RowScale make_scale(int s) {
+    s = max(-2044, min(2046, s)); // shifts of finite inputs stay within +-1200; keep the exponent fields valid regardless
+    const int s1 = s / 2, s2 = s - s1;
+    RowScale r;
+    r.f1 = __longlong_as_double((long long)(1023 + s1) << 52);
+    r.f2 = __longlong_as_double((long long)(1023 + s2) << 52);
     return r;
 }
+// trunc(a * 2^s): both products are exact whenever the result is >= 1 in magnitude ("split")
+template <typename U> __device__ __forceinline__ double scaled_trunc(U a, const RowScale &sc) {
+    return trunc(__dmul_rn(__dmul_rn((double)a, sc.f1), sc.f2));
+}
+__device__ __forceinline__ double group_rem(double x, double M, double invM) {
+    const double q = __dadd_rn(__fma_rn(x, invM, kMagic), -kMagic);
+    return __fma_rn(-M, q, x);
+}
+template <bool LARGE> __device__ __forceinline__ double level1(double x, int g) {
+    const double M = g8d_grpM[g], invM = g8d_grpInvM[g];
+    if constexpr (LARGE) x = group_rem(x, M * 1048576.0, invM * (1.0 / 1048576.0));
+    return group_rem(x, M, invM);
+}
+// symmetric residue (as int32; the low byte is the int8 plane value) of the level-1 remainder r modulo moduli[idx]
+__device__ __forceinline__ int32_t level2(double r, int idx) {
+    const int32_t a1  = __double2loint(__dadd_rn(r, g8d_mbias[idx]));
+    const uint32_t q  = __umulhi((uint32_t)a1, g8d_mmagic[idx]);
+    return (a1 - g8d_mhalf[idx]) - (int32_t)(q * (uint32_t)g8d_moduli[INT8][idx]);
+}
+// x mod 256 (only the low byte is meaningful)
+__device__ __forceinline__ int32_t residue256(double x) {
+    return __double2loint(__dadd_rn(group_rem(x, 4294967296.0, 1.0 / 4294967296.0), kMagic));
+}
+// bytes {a, b, c, d}.b0 -> one 32-bit word
+__device__ __forceinline__ uint32_t pack4(int32_t a, int32_t b, int32_t c, int32_t d) {
+    return __byte_perm(__byte_perm((uint32_t)a, (uint32_t)b, 0x0040), __byte_perm((uint32_t)c, (uint32_t)d, 0x0040), 0x5410);
+}
+// (Re + Im) mod p, symmetric, from the two symmetric residues (mod.hpp:327)
+__device__ __forceinline__ int32_t add_wrap(int32_t r, int32_t q, int32_t p) {
+    return sym_wrap((int)(int8_t)r + (int)(int8_t)q, p);
+}
 
-template <int REGIME> __device__ __forceinline__ int32_t residue(const Scaled &x, int idx, int32_t p) {
-    if constexpr (REGIME == 0) {
-        return mod_i32((int32_t)x.v, p, g8d_pinv32[INT8][idx]);
-    } else if constexpr (REGIME == 1) {
-        return mod_i64(x.v, p, g8d_pinv64[INT8][idx]);
-    } else {
-        const int32_t r = mod_i64(x.v, p, g8d_pinv64[INT8][idx]);
-        if (x.sh == 0) return r;
-        if (idx == 0) return 0; // p = 256 and shift > 10: multiple of 256
-        const int32_t w = g8d_modpow2[INT8][idx - 1][x.sh - 7];
-        return mod_i32(r * w, p, g8d_pinv32[INT8][idx]);
+// One thread's NV consecutive inner indices of one row -> all planes.  `emit(idx, g, words...)` stores NV/4 words.
+// REAL: x[NV]; planes[0].  CPLX: xr/xi; planes[0..2].
+template <bool LARGE, int NV, bool CPLX>
+__device__ __forceinline__ void split_store(const double (&xr)[NV], const double (&xi)[NV], int num_moduli, int8_t *const (&planes)[3],
+                                            size_t plane_stride, size_t off) {
+    constexpr int NW = NV / 4;
+    auto store = [&](int8_t *base, int idx, const uint32_t (&w)[NW]) {
+        int8_t *dst = base + (size_t)idx * plane_stride + off;
+        if constexpr (NW == 4) *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        else if constexpr (NW == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
+        else *reinterpret_cast<uint32_t *>(dst) = w[0];
+    };
+    // modulus 0 (p = 256)
+    {
+        uint32_t w0[NW], w1[NW], w2[NW];
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+            int32_t a[4], b[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                a[j] = residue256(xr[4 * q + j]);
+                if constexpr (CPLX) b[j] = residue256(xi[4 * q + j]);
+            }
+            w0[q] = pack4(a[0], a[1], a[2], a[3]);
+            if constexpr (CPLX) {
+                w1[q] = pack4(b[0], b[1], b[2], b[3]);
+                w2[q] = pack4(add_wrap(a[0], b[0], 256), add_wrap(a[1], b[1], 256), add_wrap(a[2], b[2], 256), add_wrap(a[3], b[3], 256));
+            }
+        }
+        store(planes[0], 0, w0);
+        if constexpr (CPLX) store(planes[1], 0, w1), store(planes[2], 0, w2);
+    }
+    const int ngroups = (num_moduli - 1 + 2) / 3;
+    for (int g = 0; g < ngroups; ++g) {
+        double rr[NV], ri[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            rr[j] = level1<LARGE>(xr[j], g);
+            if constexpr (CPLX) ri[j] = level1<LARGE>(xi[j], g);
+        }
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int idx = 3 * g + 1 + t;
+            if (idx < num_moduli) {
+                const int32_t p = g8d_moduli[INT8][idx];
+                uint32_t w0[NW], w1[NW], w2[NW];
+#pragma unroll
+                for (int q = 0; q < NW; ++q) {
+                    int32_t a[4], b[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        a[j] = level2(rr[4 * q + j], idx);
+                        if constexpr (CPLX) b[j] = level2(ri[4 * q + j], idx);
+                    }
+                    w0[q] = pack4(a[0], a[1], a[2], a[3]);
+                    if constexpr (CPLX) {
+                        w1[q] = pack4(b[0], b[1], b[2], b[3]);
+                        w2[q] = pack4(add_wrap(a[0], b[0], p), add_wrap(a[1], b[1], p), add_wrap(a[2], b[2], p), add_wrap(a[3], b[3], p));
+                    }
+                }
+                store(planes[0], idx, w0);
+                if constexpr (CPLX) store(planes[1], idx, w1), store(planes[2], idx, w2);
+            }
+        }
     }
 }
 
-__device__ __forceinline__ uint32_t pack4(int32_t a, int32_t b, int32_t c, int32_t d) {
-    return (uint32_t)(a & 0xFF) | ((uint32_t)(b & 0xFF) << 8) | ((uint32_t)(c & 0xFF) << 16) | ((uint32_t)d << 24);
+// NV consecutive inner indices of one row: either the accurate-mode bound plane(s) (MODE 2, sft = s0) or all residue planes
+template <typename T, int REGIME, int MODE, int NV>
+__device__ __forceinline__ void emit_elements(const T (&v)[NV], int sft, const SplitArgs &a, size_t off) {
+    using U             = typename Scalar<T>::U;
+    constexpr bool CPLX = Scalar<T>::cplx;
+    constexpr int NW    = NV / 4;
+    if constexpr (MODE == 2) {
+        uint32_t wr[NW], wi[NW];
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+            if constexpr (CPLX) {
+                wr[q] = pack4(upper_bound_i8<U>(v[4 * q].x, sft), upper_bound_i8<U>(v[4 * q + 1].x, sft),
+                              upper_bound_i8<U>(v[4 * q + 2].x, sft), upper_bound_i8<U>(v[4 * q + 3].x, sft));
+                wi[q] = pack4(upper_bound_i8<U>(v[4 * q].y, sft), upper_bound_i8<U>(v[4 * q + 1].y, sft),
+                              upper_bound_i8<U>(v[4 * q + 2].y, sft), upper_bound_i8<U>(v[4 * q + 3].y, sft));
+            } else {
+                wr[q] = pack4(upper_bound_i8<U>(v[4 * q], sft), upper_bound_i8<U>(v[4 * q + 1], sft),
+                              upper_bound_i8<U>(v[4 * q + 2], sft), upper_bound_i8<U>(v[4 * q + 3], sft));
+            }
+        }
+        auto st = [&](int8_t *dst, const uint32_t (&w)[NW]) {
+            if constexpr (NW == 4) *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+            else if constexpr (NW == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
+            else *reinterpret_cast<uint32_t *>(dst) = w[0];
+        };
+        st(a.planes[0] + off, wr);
+        if constexpr (CPLX) st(a.planes[1] + off, wi);
+    } else {
+        const RowScale scale = make_scale(sft);
+        double xr[NV], xi[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            if constexpr (CPLX) xr[j] = scaled_trunc<U>(v[j].x, scale), xi[j] = scaled_trunc<U>(v[j].y, scale);
+            else xr[j] = scaled_trunc<U>(v[j], scale), xi[j] = 0.0;
+        }
+        split_store<(REGIME == 2), NV, CPLX>(xr, xi, a.num_moduli, a.planes, a.plane_stride, off);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -226,67 +339,17 @@ __global__ void __launch_bounds__(256) split_rowcontig_kernel(SplitArgs a) {
         }
     }
 
-    // 4 consecutive inner indices per thread -> one 32-bit store per plane, 128 B per warp
+    // 8 consecutive inner indices per thread -> one 64-bit store per plane, 256 B per warp
+    constexpr int NV     = 8;
     const size_t row_off = (size_t)row * a.k_pad;
-    for (int l4 = threadIdx.x; l4 < (int)(a.k_pad >> 2); l4 += 256) {
-        const int l = l4 << 2;
-        T v[4];
+    for (int l = threadIdx.x * NV; l < (int)a.k_pad; l += 256 * NV) {
+        T v[NV];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NV; ++j) {
             if (l + j < k) v[j] = ldg_conj(in + l + j, a.conj);
             else v[j] = T{};
         }
-        if constexpr (MODE == 2) {
-            if constexpr (Scalar<T>::cplx) {
-                int32_t re[4], im[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    re[j] = upper_bound_i8<U>(v[j].x, sft);
-                    im[j] = upper_bound_i8<U>(v[j].y, sft);
-                }
-                uint32_t *o0 = reinterpret_cast<uint32_t *>(a.planes[0] + row_off + l);
-                uint32_t *o1 = reinterpret_cast<uint32_t *>(a.planes[1] + row_off + l);
-                *o0          = pack4(re[0], re[1], re[2], re[3]);
-                *o1          = pack4(im[0], im[1], im[2], im[3]);
-            } else {
-                uint32_t *o = reinterpret_cast<uint32_t *>(a.planes[0] + row_off + l);
-                *o = pack4(upper_bound_i8<U>(v[0], sft), upper_bound_i8<U>(v[1], sft), upper_bound_i8<U>(v[2], sft),
-                           upper_bound_i8<U>(v[3], sft));
-            }
-        } else {
-            if constexpr (Scalar<T>::cplx) {
-                Scaled xr[4], xi[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    xr[j] = scale_trunc<REGIME, U>(v[j].x, sft);
-                    xi[j] = scale_trunc<REGIME, U>(v[j].y, sft);
-                }
-                for (int i = 0; i < a.num_moduli; ++i) {
-                    const int32_t p = g8d_moduli[INT8][i];
-                    int32_t r[4], q[4], s[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        r[j] = residue<REGIME>(xr[j], i, p);
-                        q[j] = residue<REGIME>(xi[j], i, p);
-                        s[j] = sym_wrap((int)(int8_t)r[j] + (int)(int8_t)q[j], p); // (Re+Im) mod p (mod.hpp:327)
-                    }
-                    const size_t off = (size_t)i * a.plane_stride + row_off + l;
-                    *reinterpret_cast<uint32_t *>(a.planes[0] + off) = pack4(r[0], r[1], r[2], r[3]);
-                    *reinterpret_cast<uint32_t *>(a.planes[1] + off) = pack4(q[0], q[1], q[2], q[3]);
-                    *reinterpret_cast<uint32_t *>(a.planes[2] + off) = pack4(s[0], s[1], s[2], s[3]);
-                }
-            } else {
-                Scaled x[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) x[j] = scale_trunc<REGIME, U>(v[j], sft);
-                for (int i = 0; i < a.num_moduli; ++i) {
-                    const int32_t p = g8d_moduli[INT8][i];
-                    *reinterpret_cast<uint32_t *>(a.planes[0] + (size_t)i * a.plane_stride + row_off + l) =
-                        pack4(residue<REGIME>(x[0], i, p), residue<REGIME>(x[1], i, p), residue<REGIME>(x[2], i, p),
-                              residue<REGIME>(x[3], i, p));
-                }
-            }
-        }
+        emit_elements<T, REGIME, MODE, NV>(v, sft, a, row_off + l);
     }
 }
 
@@ -332,110 +395,44 @@ __global__ void __launch_bounds__(1024) stats_rowstrided_kernel(SplitArgs a) {
 // MODE 0: residues of trunc(x * 2^-sft); MODE 2: bound plane(s) with s0 = sft (as stored)
 // ------------------------------------------------------------------------------------------------
 template <typename T, int REGIME, int MODE>
-__global__ void __launch_bounds__(256) split_rowstrided_kernel(SplitArgs a) {
-    using U                = typename Scalar<T>::U;
-    constexpr bool CPLX    = Scalar<T>::cplx;
-    constexpr int TL       = 128;
+__global__ void __launch_bounds__(512) split_rowstrided_kernel(SplitArgs a) {
+    constexpr int TL = 128, NV = 8;               // tile: 32 rows x 128 inner; 16 segments of 8 per row
+    constexpr int SW = (sizeof(T) == 16) ? 0 : 1; // swizzle granularity that keeps both phases bank-conflict free
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *tile = reinterpret_cast<T *>(smem_raw); // [TL][32]
+    T *tile = reinterpret_cast<T *>(smem_raw); // [TL][32], column index XOR-swizzled by the segment number
 
     const T *X     = reinterpret_cast<const T *>(a.X);
     const int r0   = blockIdx.x * 32;
     const int l0   = blockIdx.y * TL;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5; // 16 warps
 
     {
         const int r = r0 + lane;
-#pragma unroll 4
-        for (int j = 0; j < TL / 8; ++j) {
-            const int ll = warp + 8 * j;
+#pragma unroll
+        for (int j = 0; j < TL / 16; ++j) {
+            const int ll = warp + 16 * j;
             const int l  = l0 + ll;
             T v{};
             if (r < (int)a.rows && l < (int)a.inner) v = ldg_conj(X + (size_t)l * a.ld + r, a.conj);
-            tile[ll * 32 + (lane ^ ((ll >> 4) << 2))] = v;
+            tile[ll * 32 + (lane ^ ((ll >> 3) << SW))] = v;
         }
     }
     __syncthreads();
 
-    const int rr  = threadIdx.x >> 3; // 0..31
-    const int seg = threadIdx.x & 7;  // 16 inner indices each
+    const int rr  = threadIdx.x >> 4; // 0..31
+    const int seg = threadIdx.x & 15; // 8 inner indices each
     const int row = r0 + rr;
     if (row >= (int)a.rows) return;
     const int sft = (MODE == 0) ? -(int)a.sft[row] : (int)a.sft[row];
-    const size_t off = (size_t)row * a.k_pad + l0 + seg * 16;
-    if (l0 + seg * 16 >= (int)a.k_pad) return;
+    const size_t off = (size_t)row * a.k_pad + l0 + seg * NV;
 
-    T v[16];
+    T v[NV];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const int ll = seg * 16 + j;
-        v[j]         = tile[ll * 32 + (rr ^ ((ll >> 4) << 2))];
+    for (int j = 0; j < NV; ++j) {
+        const int ll = seg * NV + j;
+        v[j]         = tile[ll * 32 + (rr ^ (seg << SW))];
     }
-
-    if constexpr (MODE == 2) {
-        if constexpr (CPLX) {
-            uint32_t wr[4], wi[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                wr[q] = pack4(upper_bound_i8<U>(v[4 * q].x, sft), upper_bound_i8<U>(v[4 * q + 1].x, sft),
-                              upper_bound_i8<U>(v[4 * q + 2].x, sft), upper_bound_i8<U>(v[4 * q + 3].x, sft));
-                wi[q] = pack4(upper_bound_i8<U>(v[4 * q].y, sft), upper_bound_i8<U>(v[4 * q + 1].y, sft),
-                              upper_bound_i8<U>(v[4 * q + 2].y, sft), upper_bound_i8<U>(v[4 * q + 3].y, sft));
-            }
-            *reinterpret_cast<uint4 *>(a.planes[0] + off) = make_uint4(wr[0], wr[1], wr[2], wr[3]);
-            *reinterpret_cast<uint4 *>(a.planes[1] + off) = make_uint4(wi[0], wi[1], wi[2], wi[3]);
-        } else {
-            uint32_t w[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                w[q] = pack4(upper_bound_i8<U>(v[4 * q], sft), upper_bound_i8<U>(v[4 * q + 1], sft),
-                             upper_bound_i8<U>(v[4 * q + 2], sft), upper_bound_i8<U>(v[4 * q + 3], sft));
-            *reinterpret_cast<uint4 *>(a.planes[0] + off) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-    } else {
-        if constexpr (CPLX) {
-            Scaled xr[16], xi[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                xr[j] = scale_trunc<REGIME, U>(v[j].x, sft);
-                xi[j] = scale_trunc<REGIME, U>(v[j].y, sft);
-            }
-            for (int i = 0; i < a.num_moduli; ++i) {
-                const int32_t p = g8d_moduli[INT8][i];
-                uint32_t w0[4], w1[4], w2[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    int32_t r[4], s[4], t[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        r[j] = residue<REGIME>(xr[4 * q + j], i, p);
-                        s[j] = residue<REGIME>(xi[4 * q + j], i, p);
-                        t[j] = sym_wrap((int)(int8_t)r[j] + (int)(int8_t)s[j], p);
-                    }
-                    w0[q] = pack4(r[0], r[1], r[2], r[3]);
-                    w1[q] = pack4(s[0], s[1], s[2], s[3]);
-                    w2[q] = pack4(t[0], t[1], t[2], t[3]);
-                }
-                const size_t o = (size_t)i * a.plane_stride + off;
-                *reinterpret_cast<uint4 *>(a.planes[0] + o) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
-                *reinterpret_cast<uint4 *>(a.planes[1] + o) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
-                *reinterpret_cast<uint4 *>(a.planes[2] + o) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
-            }
-        } else {
-            Scaled x[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] = scale_trunc<REGIME, U>(v[j], sft);
-            for (int i = 0; i < a.num_moduli; ++i) {
-                const int32_t p = g8d_moduli[INT8][i];
-                uint32_t w[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    w[q] = pack4(residue<REGIME>(x[4 * q], i, p), residue<REGIME>(x[4 * q + 1], i, p),
-                                 residue<REGIME>(x[4 * q + 2], i, p), residue<REGIME>(x[4 * q + 3], i, p));
-                *reinterpret_cast<uint4 *>(a.planes[0] + (size_t)i * a.plane_stride + off) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-        }
-    }
+    emit_elements<T, REGIME, MODE, NV>(v, sft, a, off);
 }
 
 // complex accurate mode: third bound plane = Re - Im of the two bound planes (scaling_accu_complex.hpp:5,46)
@@ -483,7 +480,7 @@ template <typename T, int MODE> static void launch_rowstrided(const SplitArgs &a
     const size_t smem = 128 * 32 * sizeof(T);
     auto go = [&](auto kern) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<grid, 256, smem, st>>>(a);
+        kern<<<grid, 512, smem, st>>>(a);
     };
     if (MODE == 2 || regime == 0) go(split_rowstrided_kernel<T, 0, MODE>);
     else if (regime == 1) go(split_rowstrided_kernel<T, 1, MODE>);

@@ -158,5 +158,42 @@ def mod_pow2(backend: str):
     return rows
 
 
+# ---------------------------------------------------------------------------------------------
+# Tables of the split kernel's two-level modular reduction (our own scheme, no reference counterpart):
+#   level 1: r = x - M_g * rint(x / M_g) in binary64 for groups of three consecutive moduli (product M_g < 2^24),
+#   level 2: per modulus p of the group, with the integer v = r (|v| <= 0.501 M_g):
+#            a1 = v + h + K p  (>= 0),  q = floor(a1 / p) = umulhi(a1, ceil(2^32/p)),  s = (a1 - h) - q p  in [-h, h].
+# `fast_mod_tables` proves the exact-floor condition a1 * (ceil(2^32/p) p - 2^32) < 2^32 for every modulus.
+# ---------------------------------------------------------------------------------------------
+MAGIC_RINT = 1.5 * 2.0 ** 52
+GROUP_SIZE = 3
+
+
+def fast_mod_tables(backend: str = "INT8"):
+    mods = moduli(backend)
+    assert backend == "INT8" and mods[0] == 256
+    groups = [list(range(1 + GROUP_SIZE * g, min(1 + GROUP_SIZE * (g + 1), len(mods)))) for g in range((len(mods) - 1 + GROUP_SIZE - 1) // GROUP_SIZE)]
+    grpM, magic, half, bias = [], [0] * len(mods), [0] * len(mods), [0.0] * len(mods)
+    for members in groups:
+        # a short last group borrows the preceding moduli for its product so that x / M_g stays below 2^51
+        span = list(range(members[-1] - GROUP_SIZE + 1, members[-1] + 1))
+        M = 1
+        for i in span:
+            M *= mods[i]
+        assert 2 ** 21 < M < 2 ** 24
+        grpM.append(M)
+        vmax = int(0.501 * M) + 2  # |level-1 remainder| <= (0.5 + 2^-9) M
+        for i in members:
+            pm = mods[i]
+            h = pm // 2
+            K = -(-(vmax + h) // pm) + 1
+            mg = -(-(1 << 32) // pm)  # ceil(2^32 / p)
+            e = mg * pm - (1 << 32)
+            a1max = vmax + h + K * pm
+            assert 0 < e <= pm and a1max * e < (1 << 32) and a1max < 2 ** 31, (pm, e, a1max)
+            magic[i], half[i], bias[i] = mg, h, MAGIC_RINT + h + K * pm
+    return dict(groups=groups, grpM=grpM, magic=magic, half=half, bias=bias)
+
+
 def hexf(x: float) -> str:
     return float(x).hex()
