@@ -61,3 +61,17 @@ def test_native_library_missing_is_an_error(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_lib", None)
     with pytest.raises(_lib.NativeLibraryMissing):
         _lib.load()
+
+
+def test_cxx_and_hook_symbols_match_reference():
+    """lib/libgemmul8.so exports the reference library's 16 C++ symbols (nm of the compiled reference,
+    tests/golden/ref_cxx_symbols.txt) and the 6 hook symbols (hook.cu:846-1055)."""
+    import subprocess
+
+    lib = ROOT / "gemmul8_b200" / "lib" / "libgemmul8.so"
+    assert lib.exists(), "run __graft_entry__.build() first"
+    want = (ROOT / "tests/golden/ref_cxx_symbols.txt").read_text().split()
+    out = subprocess.run(["nm", "-D", "--defined-only", str(lib)], capture_output=True, text=True).stdout
+    have = set(re.findall(r" T (\S+)", out))
+    assert len(want) == 16 and set(want) <= have
+    assert {"cublasSgemm_v2", "cublasDgemm_v2", "cublasCgemm_v2", "cublasZgemm_v2", "cublasGemmEx", "cublasDestroy_v2"} <= have

@@ -1,0 +1,66 @@
+"""Drop-in checks at the reference's own boundary (C++ API + LD_PRELOAD hook), restating its sample/ and
+debug/test_hijack.cu programs with real assertions.  The programs in tests/native are compiled against THIS repo's
+include/gemmul8.hpp and lib/libgemmul8.so."""
+import os
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+NATIVE = ROOT / "tests" / "native"
+LIB = ROOT / "gemmul8_b200" / "lib" / "libgemmul8.so"
+
+
+@pytest.fixture(scope="module")
+def binaries(cuda):
+    if not (NATIVE / "_build" / "sample_kat").exists() or not (NATIVE / "_build" / "hook_check").exists():
+        subprocess.check_call(["make", "-C", str(NATIVE)])
+    return NATIVE / "_build"
+
+
+def test_cxx_api_sample_known_answer(binaries):
+    """sample/dgemm_cuBLAS{,Lt}_int8.cu through gemmul8::gemmLt and gemmul8::gemm: exact product at N=15"""
+    r = subprocess.run([str(binaries / "sample_kat")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "exact" in r.stdout, r.stdout + r.stderr
+
+
+def _run_hook(binaries, env_extra, preload):
+    env = dict(os.environ)
+    env.update(env_extra)
+    if preload:
+        env["LD_PRELOAD"] = str(LIB)
+    r = subprocess.run([str(binaries / "hook_check")], capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return [(ln.split(" checksum ")[0], float(ln.split(" checksum ")[1])) for ln in r.stdout.splitlines() if " checksum " in ln], r.stderr
+
+
+def test_ld_preload_hook_matches_native_cublas(binaries):
+    native, _ = _run_hook(binaries, {}, False)
+    assert len(native) == 6
+    # not enabled (NUM_MOD unset -> 0): every call must fall through to the real cuBLAS => identical bits
+    passthrough, _ = _run_hook(binaries, {}, True)
+    assert passthrough == native
+    base = {"GEMMUL8_NUM_MOD_D": "15", "GEMMUL8_NUM_MOD_S": "8"}
+    for extra in ({}, {"GEMMUL8_FASTMODE_D": "1", "GEMMUL8_FASTMODE_S": "1"},
+                  {"GEMMUL8_SKIP_SCALE_A": "1", "GEMMUL8_SKIP_SCALE_B": "1", "GEMMUL8_MAX_M": "128", "GEMMUL8_MAX_N": "128",
+                   "GEMMUL8_MAX_K": "128", "GEMMUL8_MAX_NUM_MOD": "15"}):
+        emu, err = _run_hook(binaries, {**base, **extra}, True)
+        assert "failed" not in err, err
+        assert [a for a, _ in emu] == [a for a, _ in native]
+        for (name, x), (_, y) in zip(emu, native):
+            tol = 2e-5 if name.startswith("sgemm") else (1e-9 if "FASTMODE_D" in extra else 1e-11)
+            assert abs(x - y) <= tol * max(1.0, abs(y)), (name, x, y, extra)
+    # out-of-range moduli count -> native path again (hook.cu:625-629)
+    off, _ = _run_hook(binaries, {"GEMMUL8_NUM_MOD_D": "21", "GEMMUL8_NUM_MOD_S": "14"}, True)
+    assert off == native
+
+
+def test_exported_symbols_match_reference():
+    want = (ROOT / "tests/golden/ref_cxx_symbols.txt").read_text().split()
+    out = subprocess.run(["nm", "-D", "--defined-only", str(LIB)], capture_output=True, text=True).stdout
+    have = set(re.findall(r" T (\S+)", out))
+    assert set(want) <= have
+    assert {"cublasSgemm_v2", "cublasDgemm_v2", "cublasCgemm_v2", "cublasZgemm_v2", "cublasGemmEx", "cublasDestroy_v2"} <= have
