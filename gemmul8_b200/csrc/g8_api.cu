@@ -192,16 +192,48 @@ static int gemm_impl(const g8_gemm_desc &d, double *phase_ns) {
     return (int)cudaPeekAtLastError();
 }
 
-// C_hi (int32, summed over K-shards) -> symmetric residues
-__global__ void requant_i32_kernel(const int32_t *__restrict__ C_hi, size_t count4, int first_modulus, int8_t *__restrict__ C_mid) {
+// ---- K-sharded multi-GPU helpers (no reference counterpart; arithmetic = conv_hi2mid_real.hpp:19-22) ----
+// C_hi (int32, summed over K-shards) -> symmetric residues.  4 consecutive rows per thread.
+__global__ void requant_i32_kernel(const int32_t *__restrict__ C_hi, size_t rows4, size_t cols, size_t in_ld, size_t in_unit_stride,
+                                   int first_modulus, int8_t *__restrict__ C_mid, size_t out_ld, size_t out_unit_stride) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count4) return;
+    if (i >= rows4 * cols) return;
+    const size_t col = i / rows4, r4 = (i - col * rows4) * 4;
     const int u     = blockIdx.y;
     const int32_t p = g8d_moduli[INT8][first_modulus + u], pinv = g8d_pinv32[INT8][first_modulus + u];
-    const int4 v    = reinterpret_cast<const int4 *>(C_hi)[(size_t)u * count4 + i];
+    const int4 v    = *reinterpret_cast<const int4 *>(C_hi + (size_t)u * in_unit_stride + col * in_ld + r4);
     const int32_t a = mod_i32(v.x, p, pinv), b = mod_i32(v.y, p, pinv), c = mod_i32(v.z, p, pinv), e = mod_i32(v.w, p, pinv);
-    reinterpret_cast<uint32_t *>(C_mid)[(size_t)u * count4 + i] =
+    *reinterpret_cast<uint32_t *>(C_mid + (size_t)u * out_unit_stride + col * out_ld + r4) =
         (uint32_t)(a & 0xFF) | ((uint32_t)(b & 0xFF) << 8) | ((uint32_t)(c & 0xFF) << 16) | ((uint32_t)e << 24);
+}
+// sum of `nparts` int8 residue arrays (one per K-shard, identical layout) reduced mod p again
+__global__ void residue_sum_kernel(const int8_t *__restrict__ parts, int nparts, size_t part_stride, size_t rows4, size_t cols, size_t in_ld,
+                                   size_t in_unit_stride, int first_modulus, int8_t *__restrict__ C_mid, size_t out_ld, size_t out_unit_stride) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows4 * cols) return;
+    const size_t col = i / rows4, r4 = (i - col * rows4) * 4;
+    const int u     = blockIdx.y;
+    const int32_t p = g8d_moduli[INT8][first_modulus + u], pinv = g8d_pinv32[INT8][first_modulus + u];
+    int32_t acc[4] = {0, 0, 0, 0};
+    for (int q = 0; q < nparts; ++q) {
+        const char4 v = *reinterpret_cast<const char4 *>(parts + (size_t)q * part_stride + (size_t)u * in_unit_stride + col * in_ld + r4);
+        acc[0] += v.x, acc[1] += v.y, acc[2] += v.z, acc[3] += v.w;
+    }
+    const int32_t a = mod_i32(acc[0], p, pinv), b = mod_i32(acc[1], p, pinv), c = mod_i32(acc[2], p, pinv), e = mod_i32(acc[3], p, pinv);
+    *reinterpret_cast<uint32_t *>(C_mid + (size_t)u * out_unit_stride + col * out_ld + r4) =
+        (uint32_t)(a & 0xFF) | ((uint32_t)(b & 0xFF) << 8) | ((uint32_t)(c & 0xFF) << 16) | ((uint32_t)e << 24);
+}
+// row / column maxima of an int32 slab (the reduced bound product of accurate mode); one block per column
+__global__ void maxabs_i32_kernel(const int32_t *__restrict__ C, size_t rows, size_t ld, int32_t *__restrict__ rowmax, int32_t *__restrict__ colmax) {
+    const int32_t *col = C + (size_t)blockIdx.x * ld;
+    int32_t cm = 0;
+    for (size_t r = threadIdx.x; r < rows; r += blockDim.x) {
+        const int32_t v = col[r];
+        cm = max(cm, v);
+        if (v > 0) atomicMax(&rowmax[r], v);
+    }
+    cm = __reduce_max_sync(0xffffffffu, cm);
+    if ((threadIdx.x & 31) == 0 && cm > 0) atomicMax(&colmax[blockIdx.x], cm);
 }
 
 } // namespace g8
@@ -230,7 +262,7 @@ __attribute__((visibility("default"))) int g8_stage_split(int dtype, int is_A, i
     if (!X || !sft || !planes || dtype < F32 || dtype > C64 || num_moduli < 2 || num_moduli > G8_MAX_MODULI) return G8_STATUS_INVALID_VALUE;
     if (rows == 0 || k == 0) return 0;
     SplitArgs a = split_args(is_A, op, rows, k, X, ld, num_moduli, sft, planes, plane_stride_bytes, group_stride_planes);
-    if (mode == 2)
+    if (mode >= 2)
         for (int g = 0; g < 3; ++g) a.planes[g] = planes + g * plane_stride_bytes;
     launch_split(a, dtype, mode, static_cast<cudaStream_t>(stream));
     return (int)cudaGetLastError();
@@ -266,13 +298,53 @@ __attribute__((visibility("default"))) int g8_stage_crt(int dtype, const void *C
     return launch_crt(c, dtype, static_cast<cudaStream_t>(stream));
 }
 
-__attribute__((visibility("default"))) int g8_stage_requant_i32(const int32_t *C_hi, size_t count_per_plane, int num_units, int first_modulus, int8_t *C_mid, void *stream) {
+__attribute__((visibility("default"))) int g8_stage_requant_i32(const int32_t *C_hi, size_t rows, size_t cols, size_t in_ld, size_t in_unit_stride, int num_units,
+                         int first_modulus, int8_t *C_mid, size_t out_ld, size_t out_unit_stride, void *stream) {
     if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
-    if (count_per_plane % 4) return G8_STATUS_INVALID_VALUE;
-    if (count_per_plane == 0 || num_units == 0) return 0;
-    const size_t c4 = count_per_plane / 4;
-    const dim3 grid((unsigned)((c4 + 255) / 256), (unsigned)num_units);
-    requant_i32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(C_hi, c4, first_modulus, C_mid);
+    if (!C_hi || !C_mid || rows % 4 || in_ld % 4 || out_ld % 4 || in_unit_stride % 4 || out_unit_stride % 4) return G8_STATUS_INVALID_VALUE;
+    if (rows == 0 || cols == 0 || num_units == 0) return 0;
+    const size_t r4 = rows / 4;
+    const dim3 grid((unsigned)((r4 * cols + 255) / 256), (unsigned)num_units);
+    requant_i32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(C_hi, r4, cols, in_ld, in_unit_stride, first_modulus, C_mid, out_ld,
+                                                                            out_unit_stride);
+    return (int)cudaGetLastError();
+}
+
+__attribute__((visibility("default"))) int g8_stage_residue_sum(const int8_t *parts, int nparts, size_t part_stride, size_t rows, size_t cols, size_t in_ld, size_t in_unit_stride,
+                         int num_units, int first_modulus, int8_t *C_mid, size_t out_ld, size_t out_unit_stride, void *stream) {
+    if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
+    if (!parts || !C_mid || nparts < 1 || nparts > 64 || rows % 4 || in_ld % 4 || out_ld % 4 || in_unit_stride % 4 || out_unit_stride % 4 || part_stride % 4)
+        return G8_STATUS_INVALID_VALUE;
+    if (rows == 0 || cols == 0 || num_units == 0) return 0;
+    const size_t r4 = rows / 4;
+    const dim3 grid((unsigned)((r4 * cols + 255) / 256), (unsigned)num_units);
+    residue_sum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(parts, nparts, part_stride, r4, cols, in_ld, in_unit_stride, first_modulus,
+                                                                            C_mid, out_ld, out_unit_stride);
+    return (int)cudaGetLastError();
+}
+
+__attribute__((visibility("default"))) int g8_stage_maxabs_i32(const int32_t *C, size_t rows, size_t cols, size_t ld, int32_t *rowmax, int32_t *colmax, void *stream) {
+    if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
+    if (!C || !rowmax || !colmax) return G8_STATUS_INVALID_VALUE;
+    if (rows == 0 || cols == 0) return 0;
+    maxabs_i32_kernel<<<(unsigned)cols, 256, 0, static_cast<cudaStream_t>(stream)>>>(C, rows, ld, rowmax, colmax);
+    return (int)cudaGetLastError();
+}
+
+__attribute__((visibility("default"))) int g8_stage_stats(int dtype, int is_A, int op, size_t rows, size_t k, const void *X, size_t ld, double *amax, double *sumsq, void *stream) {
+    if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
+    if (!X || !amax || !sumsq || dtype < F32 || dtype > C64) return G8_STATUS_INVALID_VALUE;
+    if (rows == 0) return 0;
+    SplitArgs a = split_args(is_A, op, rows, k, X, ld, 2, nullptr, nullptr, 0, 0);
+    launch_stats(a, dtype, amax, sumsq, static_cast<cudaStream_t>(stream));
+    return (int)cudaGetLastError();
+}
+
+__attribute__((visibility("default"))) int g8_stage_shift_from_stats(const double *amax, const double *sumsq, size_t count, unsigned num_moduli, int kind, int16_t *sft, void *stream) {
+    if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
+    if (!amax || !sft || (kind == 0 && !sumsq) || num_moduli < 2 || num_moduli > G8_MAX_MODULI) return G8_STATUS_INVALID_VALUE;
+    if (count == 0) return 0;
+    launch_shift_from_stats(amax, sumsq, count, (int)num_moduli, kind, sft, static_cast<cudaStream_t>(stream));
     return (int)cudaGetLastError();
 }
 

@@ -20,6 +20,9 @@ struct SplitArgs {
 };
 void launch_split(const SplitArgs &a, int dtype, int mode, cudaStream_t st);
 void launch_finalize_accu_shift(int16_t *sft, const int32_t *cmax, size_t count, int num_moduli, cudaStream_t st);
+// K-sharded multi-GPU support
+void launch_stats(const SplitArgs &a, int dtype, double *amax, double *sumsq, cudaStream_t st);
+void launch_shift_from_stats(const double *amax, const double *sumsq, size_t count, int num_moduli, int kind, int16_t *sft, cudaStream_t st);
 
 // ---- stage 2: low-precision GEMMs -------------------------------------------------------------
 // One "unit" is one output tile set: for unit u the kernel accumulates `nchain` products

@@ -300,6 +300,8 @@ __global__ void __launch_bounds__(256) split_rowcontig_kernel(SplitArgs a) {
 
     if constexpr (MODE == 0) {
         sft = -(int)a.sft[row];
+    } else if constexpr (MODE == 3) {
+        sft = (int)a.sft[row]; // bound planes with an externally supplied s0 (K-sharded runs: s0 comes from the GLOBAL amax)
     } else {
         // thread t visits l = t, t+256, ... in order (find_max.hpp:272-277 / 26-38)
         U amax = 0, sum = 0;
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__(256) split_rowcontig_kernel(SplitArgs a) {
             if (l + j < k) v[j] = ldg_conj(in + l + j, a.conj);
             else v[j] = T{};
         }
-        emit_elements<T, REGIME, MODE, NV>(v, sft, a, row_off + l);
+        emit_elements<T, REGIME, (MODE == 3 ? 2 : MODE), NV>(v, sft, a, row_off + l);
     }
 }
 
@@ -435,19 +437,6 @@ __global__ void __launch_bounds__(512) split_rowstrided_kernel(SplitArgs a) {
     emit_elements<T, REGIME, MODE, NV>(v, sft, a, off);
 }
 
-// complex accurate mode: third bound plane = Re - Im of the two bound planes (scaling_accu_complex.hpp:5,46)
-__global__ void bound_diff_kernel(const int8_t *__restrict__ re, const int8_t *__restrict__ im, int8_t *__restrict__ out, size_t n16) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n16) return;
-    const uint4 a = reinterpret_cast<const uint4 *>(re)[i], b = reinterpret_cast<const uint4 *>(im)[i];
-    uint4 o;
-    o.x = __vsub4(a.x, b.x);
-    o.y = __vsub4(a.y, b.y);
-    o.z = __vsub4(a.z, b.z);
-    o.w = __vsub4(a.w, b.w);
-    reinterpret_cast<uint4 *>(out)[i] = o;
-}
-
 // accurate mode, stage (iii): sft = -(s0 + floor(fmaf_rd(-0x1.000006p-1f, log2f(float(max)), log2P)))
 // (scaling_accu_real.hpp:6-11,157-159,202-204); max[] was filled by the bound GEMM's atomicMax epilogue.
 __global__ void finalize_accu_shift_kernel(int16_t *__restrict__ sft, const int32_t *__restrict__ cmax, int count, int num_moduli) {
@@ -470,7 +459,7 @@ static int regime_of(int num_moduli) {
 
 template <typename T, int MODE> static void launch_rowcontig(const SplitArgs &a, int regime, cudaStream_t st) {
     const dim3 grid((unsigned)a.rows);
-    if (MODE == 2 || regime == 0) split_rowcontig_kernel<T, 0, MODE><<<grid, 256, 0, st>>>(a);
+    if (MODE >= 2 || regime == 0) split_rowcontig_kernel<T, 0, MODE><<<grid, 256, 0, st>>>(a);
     else if (regime == 1) split_rowcontig_kernel<T, 1, MODE><<<grid, 256, 0, st>>>(a);
     else split_rowcontig_kernel<T, 2, MODE><<<grid, 256, 0, st>>>(a);
 }
@@ -492,21 +481,19 @@ template <typename T> static void split_typed(const SplitArgs &a, int mode, cuda
     if (a.row_contig) {
         if (mode == 0) launch_rowcontig<T, 0>(a, regime, st);
         else if (mode == 1) launch_rowcontig<T, 1>(a, regime, st);
-        else launch_rowcontig<T, 2>(a, regime, st);
+        else if (mode == 2) launch_rowcontig<T, 2>(a, regime, st);
+        else launch_rowcontig<T, 3>(a, regime, st);
     } else {
         const dim3 sgrid((unsigned)((a.rows + 31) / 32)), sblock(32, 32);
         if (mode == 1) stats_rowstrided_kernel<T, 1><<<sgrid, sblock, 0, st>>>(a);
         if (mode == 2) stats_rowstrided_kernel<T, 2><<<sgrid, sblock, 0, st>>>(a);
-        if (mode == 2) launch_rowstrided<T, 2>(a, regime, st);
+        if (mode >= 2) launch_rowstrided<T, 2>(a, regime, st);
         else launch_rowstrided<T, 0>(a, regime, st);
-    }
-    if (mode == 2 && Scalar<T>::cplx) {
-        const size_t n16 = a.rows * a.k_pad / 16;
-        bound_diff_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>(a.planes[0], a.planes[1], a.planes[2], n16);
     }
 }
 
-// mode 0: split with stored shifts, 1: fast (shift + split), 2: accurate stage (i) (s0 + bound planes)
+// mode 0: split with stored shifts, 1: fast (shift + split), 2: accurate stage (i) (s0 + bound planes),
+// 3: bound planes with the stored s0 (no statistics pass)
 void launch_split(const SplitArgs &a, int dtype, int mode, cudaStream_t st) {
     switch (dtype) {
     case F32: split_typed<float>(a, mode, st); break;
@@ -514,6 +501,83 @@ void launch_split(const SplitArgs &a, int dtype, int mode, cudaStream_t st) {
     case C32: split_typed<float2>(a, mode, st); break;
     case C64: split_typed<double2>(a, mode, st); break;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-sharded multi-GPU support: local row statistics as doubles, and shifts from (globally reduced) statistics.
+// There is no reference counterpart (the reference is single-GPU); the shift formulas are the reference's.
+// ------------------------------------------------------------------------------------------------
+template <typename T> __global__ void __launch_bounds__(256) stats_only_rowcontig_kernel(SplitArgs a, double *amax_out, double *sumsq_out) {
+    using U     = typename Scalar<T>::U;
+    const T *in = reinterpret_cast<const T *>(a.X) + (size_t)blockIdx.x * a.ld;
+    __shared__ double s_max[8], s_sum[8];
+    U amax = 0;
+    double sum = 0;
+    for (int l = threadIdx.x; l < (int)a.inner; l += 256) {
+        const T v = __ldg(in + l);
+        acc_amax<T>(v, amax);
+        if constexpr (Scalar<T>::cplx) sum = __fma_ru((double)v.y, (double)v.y, __fma_ru((double)v.x, (double)v.x, sum));
+        else sum = __fma_ru((double)v, (double)v, sum);
+    }
+    double dmax = warp_max((double)amax);
+    sum         = warp_sum_ru(sum);
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = dmax, s_sum[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) dmax = max(dmax, s_max[w]), sum = __dadd_ru(sum, s_sum[w]);
+        amax_out[blockIdx.x] = dmax, sumsq_out[blockIdx.x] = sum;
+    }
+}
+template <typename T> __global__ void __launch_bounds__(1024) stats_only_rowstrided_kernel(SplitArgs a, double *amax_out, double *sumsq_out) {
+    using U = typename Scalar<T>::U;
+    __shared__ double s_max[32][33], s_sum[32][33];
+    const T *X  = reinterpret_cast<const T *>(a.X);
+    const int x = threadIdx.x, y = threadIdx.y;
+    int row     = blockIdx.x * 32 + x;
+    U amax = 0;
+    double sum = 0;
+    if (row < (int)a.rows)
+        for (int l = y; l < (int)a.inner; l += 32) {
+            const T v = __ldg(X + row + (size_t)l * a.ld);
+            acc_amax<T>(v, amax);
+            if constexpr (Scalar<T>::cplx) sum = __fma_ru((double)v.y, (double)v.y, __fma_ru((double)v.x, (double)v.x, sum));
+            else sum = __fma_ru((double)v, (double)v, sum);
+        }
+    s_max[y][x] = (double)amax, s_sum[y][x] = sum;
+    __syncthreads();
+    const double dmax = warp_max(s_max[x][y]);
+    sum               = warp_sum_ru(s_sum[x][y]);
+    row               = blockIdx.x * 32 + y;
+    if (row < (int)a.rows && x == 0) amax_out[row] = dmax, sumsq_out[row] = sum;
+}
+// kind 0: fast-mode shift from (amax, sumsq); kind 1: accurate-mode s0 from amax
+__global__ void shift_from_stats_kernel(const double *amax, const double *sumsq, int count, int num_moduli, int kind, int16_t *sft) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    if (kind == 0) {
+        // the cross-rank sum was rounded to nearest: nudge it up so the Cauchy-Schwarz bound stays rigorous
+        const double s = sumsq[i] * (1.0 + 0x1p-48);
+        sft[i] = (int16_t)(-fast_shift(amax[i], s, g8d_log2P[INT8][num_moduli]));
+    } else {
+        sft[i] = (int16_t)accu_s0(amax[i]);
+    }
+}
+
+void launch_stats(const SplitArgs &a, int dtype, double *amax, double *sumsq, cudaStream_t st) {
+    const dim3 sgrid((unsigned)((a.rows + 31) / 32)), sblock(32, 32);
+#define G8_STATS(T)                                                                                         \
+    if (a.row_contig) stats_only_rowcontig_kernel<T><<<(unsigned)a.rows, 256, 0, st>>>(a, amax, sumsq);    \
+    else stats_only_rowstrided_kernel<T><<<sgrid, sblock, 0, st>>>(a, amax, sumsq);
+    switch (dtype) {
+    case F32: G8_STATS(float) break;
+    case F64: G8_STATS(double) break;
+    case C32: G8_STATS(float2) break;
+    case C64: G8_STATS(double2) break;
+    }
+#undef G8_STATS
+}
+void launch_shift_from_stats(const double *amax, const double *sumsq, size_t count, int num_moduli, int kind, int16_t *sft, cudaStream_t st) {
+    shift_from_stats_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(amax, sumsq, (int)count, num_moduli, kind, sft);
 }
 
 void launch_finalize_accu_shift(int16_t *sft, const int32_t *cmax, size_t count, int num_moduli, cudaStream_t st) {

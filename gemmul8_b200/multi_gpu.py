@@ -1,0 +1,206 @@
+"""K-sharded multi-GPU emulated GEMM (BASELINE.json config 3).  One process per GPU,
+`torch.distributed` (NCCL over NVLink 5 / NVSwitch) for the exchange steps, the C-ABI stage kernels for all numerics.
+
+The reference is single-GPU; this entry point is new work.  Rank r owns a K-slab of both operands,
+    A_r = op(A)[:, K_r]   (m x k_r)        B_r = op(B)[K_r, :]   (k_r x n)
+and the exact integer structure of Ozaki-II makes the sharding exact:
+
+  shifts    fast    : local row statistics (max |x|, round-up sum x^2)  -> all_reduce(MAX / SUM) -> reference shift formula
+            accurate: all_reduce(MAX) of max |x| -> s0; local bound planes; INT32 bound partial -> reduce_scatter(SUM) ->
+                      slab row/col maxima -> all_reduce(MAX) / all_gather -> final shifts   (identical on every rank, and
+                      identical to a single-GPU run on the concatenated operands: max and integer sums are order-free)
+  split     local, with the global shifts (`g8_stage_split` mode 0)
+  contraction  local tcgen05 INT8 GEMMs over all moduli; then ONE collective:
+            variant "int32"  : raw INT32 partials [col][modulus][row]  -> reduce_scatter(SUM, int32)   (the north-star wording)
+            variant "residue": partials reduced mod p in the GEMM epilogue (int8) -> all_to_all (4x fewer bytes) -> sum + mod
+  CRT       every rank reconstructs its column slab C[:, n_r] (`g8_stage_crt`)
+
+Exactness: |sum| <= K_total * 2^14 < 2^31 for K_total <= 2^17, so the INT32 reduction cannot overflow; the residue variant
+sums at most `world` int8 values.  The result of accurate mode is bit-identical to the single-GPU call on the full K.
+
+The numerics live behind a small `Stages` interface: `CudaStages` (product) drives the C ABI; tests substitute a CPU
+implementation built on the oracle to exercise THIS file's orchestration with the gloo backend.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import api
+from . import tables as T
+
+
+def pad256(x: int) -> int:
+    return 256 * ((x + 255) // 256)
+
+
+class CudaStages:
+    """Stage kernels through include/gemmul8_c.h on CUDA tensors.  No fallback: fails if the library or an sm_100a device is missing."""
+
+    def __init__(self, dtype, num_moduli, device):
+        from . import _lib
+
+        self.lib = _lib.load()
+        self.dtype, self.N, self.dev = dtype, num_moduli, torch.device(device)
+        self.dt = api._DTYPES[dtype]
+
+    def _s(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def empty(self, n, dtype):
+        return torch.empty(n, dtype=dtype, device=self.dev)
+
+    def zeros(self, n, dtype):
+        return torch.zeros(n, dtype=dtype, device=self.dev)
+
+    def stats(self, is_A, op, rows, k, X, ld):
+        amax, ss = self.empty(rows, torch.float64), self.empty(rows, torch.float64)
+        api._check(self.lib.g8_stage_stats(self.dt, int(is_A), op, rows, k, X.data_ptr(), ld, amax.data_ptr(), ss.data_ptr(), self._s()), "stats")
+        return amax, ss
+
+    def shift_from_stats(self, amax, ss, kind, sft):
+        api._check(self.lib.g8_stage_shift_from_stats(amax.data_ptr(), ss.data_ptr() if ss is not None else None, amax.numel(), self.N, kind,
+                                                      sft.data_ptr(), self._s()), "shift_from_stats")
+
+    def split(self, is_A, op, rows, k, X, ld, mode, sft, planes, plane_stride):
+        api._check(self.lib.g8_stage_split(self.dt, int(is_A), op, rows, k, X.data_ptr(), ld, self.N, mode, sft.data_ptr(), planes.data_ptr(),
+                                           plane_stride, self.N, self._s()), "split")
+
+    def gemm(self, epi, A_lo, strideA, B_lo, strideB, m, n, k_pad, units, out, out_stride, ldc):
+        api._check(self.lib.g8_stage_gemm(epi, 0, A_lo.data_ptr(), strideA, B_lo.data_ptr(), strideB, m, n, k_pad, units, 0, None, None,
+                                          out.data_ptr(), out_stride, ldc, None, None, self._s()), "gemm")
+
+    def maxabs(self, C, rows, cols, ld, rowmax, colmax):
+        api._check(self.lib.g8_stage_maxabs_i32(C.data_ptr(), rows, cols, ld, rowmax.data_ptr(), colmax.data_ptr(), self._s()), "maxabs")
+
+    def finalize_shift(self, sft, cmax, count):
+        api._check(self.lib.g8_stage_finalize_shift(sft.data_ptr(), cmax.data_ptr(), count, self.N, self._s()), "finalize_shift")
+
+    def requant(self, C_hi, rows, cols, in_ld, in_us, units, C_mid, out_ld, out_us):
+        api._check(self.lib.g8_stage_requant_i32(C_hi.data_ptr(), rows, cols, in_ld, in_us, units, 0, C_mid.data_ptr(), out_ld, out_us, self._s()), "requant")
+
+    def residue_sum(self, parts, nparts, part_stride, rows, cols, in_ld, in_us, units, C_mid, out_ld, out_us):
+        api._check(self.lib.g8_stage_residue_sum(parts.data_ptr(), nparts, part_stride, rows, cols, in_ld, in_us, units, 0, C_mid.data_ptr(),
+                                                 out_ld, out_us, self._s()), "residue_sum")
+
+    def crt(self, C_mid, ldmid, plane_stride, m, n, C, ldc, sftA, sftB, alpha, beta):
+        keep = []
+        pa, pb = api._scalar_ptr(alpha, self.dtype, keep), api._scalar_ptr(beta, self.dtype, keep)
+        api._check(self.lib.g8_stage_crt(self.dt, C_mid.data_ptr(), ldmid, plane_stride, m, n, self.N, C.data_ptr(), ldc, sftA.data_ptr(),
+                                         sftB.data_ptr(), pa, pb, self._s()), "crt")
+
+
+# ---- collectives (NCCL on GPUs; the gloo branches exist for the CPU tests of this orchestration) ----
+def _is_gloo(group=None):
+    return dist.get_backend(group) == "gloo"
+
+
+def reduce_scatter_sum(out, inp, group=None):
+    """out <- sum over ranks of inp[rank * out.numel() : (rank + 1) * out.numel()]"""
+    if _is_gloo(group):
+        tmp = inp.clone()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+        r = dist.get_rank(group)
+        out.copy_(tmp[r * out.numel():(r + 1) * out.numel()])
+    else:
+        dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group)
+
+
+def all_to_all(out, inp, group=None):
+    if _is_gloo(group):
+        W = dist.get_world_size(group)
+        gathered = [torch.empty_like(inp) for _ in range(W)]
+        dist.all_gather(gathered, inp, group=group)
+        r, c = dist.get_rank(group), out.numel() // W
+        for j in range(W):
+            out[j * c:(j + 1) * c].copy_(gathered[j][r * c:(r + 1) * c])
+    else:
+        dist.all_to_all_single(out, inp, group=group)
+
+
+class KShardGemm:
+    """C[:, slab(rank)] = alpha * sum_r A_r B_r (+ beta * C) for real S/D GEMM, op N/N layout of the local slabs
+    (A_r: m x k_local column-major with ld = m; B_r: k_local x n column-major with ld = k_local).
+    n must be a multiple of the world size (each rank reconstructs n / world columns)."""
+
+    def __init__(self, m, n, k_local, num_moduli, fastmode=False, dtype=torch.float64, device=None, variant="int32", stages=None,
+                 group=None):
+        if dtype not in (torch.float32, torch.float64):
+            raise NotImplementedError("K-sharded path: real S/D GEMM only")
+        self.group = group
+        self.W, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if n % self.W:
+            raise ValueError("n must be divisible by the world size")
+        self.m, self.n, self.k, self.N = m, n, k_local, num_moduli
+        self.fast, self.dtype, self.variant = bool(fastmode), dtype, variant
+        self.st = stages if stages is not None else CudaStages(dtype, num_moduli, device)
+        self.m_pad, self.k_pad, self.n_pad = pad256(m), pad256(k_local), pad256(n)
+        self.nc = n // self.W
+        self.sizeA, self.sizeB = self.k_pad * self.m_pad, self.k_pad * n
+        st, N = self.st, num_moduli
+        self.A_lo = st.empty(self.sizeA * N, torch.int8)
+        self.B_lo = st.empty(self.sizeB * N, torch.int8)
+        self.sftA = st.zeros(self.m_pad, torch.int16)
+        self.sftB = st.zeros(self.n_pad, torch.int16)
+        per = n * N * self.m_pad
+        self.part = st.empty(per, torch.int32 if variant == "int32" else torch.int8)      # [col][modulus][row]
+        self.recv = st.empty(per // self.W if variant == "int32" else per, self.part.dtype)  # my column slab (x world for residue)
+        self.C_mid = st.empty(N * self.nc * self.m_pad, torch.int8)                         # [modulus][col][row]
+        if not self.fast:
+            self.cbar = st.empty(n * self.m_pad, torch.int32)
+            self.cbar_slab = st.empty(self.nc * self.m_pad, torch.int32)
+        self.local_out_elems = m * self.nc
+
+    def local_out(self, C):
+        return C[:self.local_out_elems]
+
+    def _shifts(self, A, B):
+        st, m, n, k, N = self.st, self.m, self.n, self.k, self.N
+        amaxA, ssA = st.stats(True, 0, m, k, A, m)
+        amaxB, ssB = st.stats(False, 0, n, k, B, k)
+        both_max = torch.cat([amaxA, amaxB])
+        dist.all_reduce(both_max, op=dist.ReduceOp.MAX, group=self.group)
+        amaxA, amaxB = both_max[:m], both_max[m:]
+        if self.fast:
+            both_ss = torch.cat([ssA, ssB])
+            dist.all_reduce(both_ss, op=dist.ReduceOp.SUM, group=self.group)
+            st.shift_from_stats(amaxA.contiguous(), both_ss[:m].contiguous(), 0, self.sftA)
+            st.shift_from_stats(amaxB.contiguous(), both_ss[m:].contiguous(), 0, self.sftB)
+            return
+        # accurate: s0 from the global max, bound planes (aliasing plane 0), bound partial, reduce, maxima, final shifts
+        st.shift_from_stats(amaxA.contiguous(), None, 1, self.sftA)
+        st.shift_from_stats(amaxB.contiguous(), None, 1, self.sftB)
+        st.split(True, 0, m, k, A, m, 3, self.sftA, self.A_lo, self.sizeA)
+        st.split(False, 0, n, k, B, k, 3, self.sftB, self.B_lo, self.sizeB)
+        st.gemm(1, self.A_lo, self.sizeA, self.B_lo, self.sizeB, m, n, self.k_pad, 1, self.cbar, 0, self.m_pad)
+        reduce_scatter_sum(self.cbar_slab, self.cbar, self.group)
+        rowmax = st.zeros(self.m_pad, torch.int32)
+        colmax_slab = st.zeros(self.nc, torch.int32)
+        st.maxabs(self.cbar_slab, m, self.nc, self.m_pad, rowmax, colmax_slab)
+        dist.all_reduce(rowmax, op=dist.ReduceOp.MAX, group=self.group)
+        colmax = st.zeros(self.n, torch.int32)
+        dist.all_gather_into_tensor(colmax, colmax_slab, group=self.group) if not _is_gloo(self.group) else \
+            dist.all_gather(list(colmax.view(self.W, self.nc).unbind(0)), colmax_slab, group=self.group)
+        st.finalize_shift(self.sftA, rowmax, m)
+        st.finalize_shift(self.sftB, colmax, n)
+
+    def run(self, A, B, C, alpha=1.0, beta=0.0):
+        """A: flat m*k_local, B: flat k_local*n (this rank's K-slab), C: flat buffer receiving the m x (n/world) slab (ld = m)."""
+        st, m, n, k, N = self.st, self.m, self.n, self.k, self.N
+        self._shifts(A, B)
+        st.split(True, 0, m, k, A, m, 0, self.sftA, self.A_lo, self.sizeA)
+        st.split(False, 0, n, k, B, k, 0, self.sftB, self.B_lo, self.sizeB)
+        mp, nc = self.m_pad, self.nc
+        if self.variant == "int32":
+            st.gemm(1, self.A_lo, self.sizeA, self.B_lo, self.sizeB, m, n, self.k_pad, N, self.part, mp, N * mp)
+            reduce_scatter_sum(self.recv, self.part, self.group)   # the single NCCL reduce of the INT32 partials
+            st.requant(self.recv, mp, nc, N * mp, mp, N, self.C_mid, mp, nc * mp)
+        else:
+            st.gemm(0, self.A_lo, self.sizeA, self.B_lo, self.sizeB, m, n, self.k_pad, N, self.part, mp, N * mp)
+            all_to_all(self.recv, self.part, self.group)
+            st.residue_sum(self.recv, self.W, nc * N * mp, mp, nc, N * mp, mp, N, self.C_mid, mp, nc * mp)
+        r0 = self.rank * nc
+        st.crt(self.C_mid, mp, nc * mp, m, nc, C, m, self.sftA, self.sftB[r0:r0 + nc], alpha, beta)
+        return C

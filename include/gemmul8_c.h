@@ -77,7 +77,7 @@ int g8_gemm(const g8_gemm_desc *d, double *phase_ns);
 /* Stage 1 for ONE operand with externally supplied shifts: planes <- trunc(op(X) * 2^-sft) mod p_i.
  * is_A selects the m x k (A) or k x n (B) role.  Replaces scalingA/B kernels (src/scaling_fast_real.hpp:54-164). */
 int g8_stage_split(int dtype, int is_A, int op, size_t rows, size_t k, const void *X, size_t ld, unsigned num_moduli,
-                   int mode /*0: use sft, 1: fast (computes sft), 2: accurate bound plane + s0*/, int16_t *sft,
+                   int mode /*0: use sft, 1: fast (computes sft), 2: accurate bound plane + s0, 3: bound plane with the given s0*/, int16_t *sft,
                    int8_t *planes, size_t plane_stride_bytes, size_t group_stride_planes, void *stream);
 
 /* accurate mode stage (iii): sft[i] = -(s0[i] + floor(log2P - 0.5000001*log2(cmax[i])))  (src/scaling_accu_real.hpp:6-11,157-159) */
@@ -94,8 +94,27 @@ int g8_stage_gemm(int epilogue, int use_simt, const int8_t *A_lo, size_t strideA
 int g8_stage_crt(int dtype, const void *C_mid, size_t ldmid, size_t plane_stride, size_t m, size_t n, unsigned num_moduli, void *C,
                  size_t ldc, const int16_t *sftA, const int16_t *sftB, const void *alpha, const void *beta, void *stream);
 
-/* C_mid[i] = sym(C_hi[i] mod p_i) for int32 planes that were summed across K-shards (src/conv_hi2mid_real.hpp:9-25) */
-int g8_stage_requant_i32(const int32_t *C_hi, size_t count_per_plane, int num_units, int first_modulus, int8_t *C_mid, void *stream);
+/* ---- K-sharded multi-GPU support (new work; the reference is single-GPU) ---- */
+
+/* C_mid[u][col][row] = sym(C_hi[u][col][row] mod p_u) for int32 partial products that were summed across K-shards
+ * (arithmetic of src/conv_hi2mid_real.hpp:9-25).  Strided so that any [col][unit][row] / [unit][col][row] layout works;
+ * rows and all strides must be multiples of 4. */
+int g8_stage_requant_i32(const int32_t *C_hi, size_t rows, size_t cols, size_t in_ld, size_t in_unit_stride, int num_units,
+                         int first_modulus, int8_t *C_mid, size_t out_ld, size_t out_unit_stride, void *stream);
+
+/* Residue variant: every shard reduced its partial mod p locally (int8); sum `nparts` such arrays and reduce again. */
+int g8_stage_residue_sum(const int8_t *parts, int nparts, size_t part_stride, size_t rows, size_t cols, size_t in_ld, size_t in_unit_stride,
+                         int num_units, int first_modulus, int8_t *C_mid, size_t out_ld, size_t out_unit_stride, void *stream);
+
+/* rowmax[r] = max(rowmax[r], C[r, c]), colmax[c] likewise, over an int32 slab (reduced bound product of accurate mode) */
+int g8_stage_maxabs_i32(const int32_t *C, size_t rows, size_t cols, size_t ld, int32_t *rowmax, int32_t *colmax, void *stream);
+
+/* Local row statistics of op(X) (rows x k view, is_A as in g8_stage_split): amax[r] = max |x|, sumsq[r] = round-up sum of x^2 */
+int g8_stage_stats(int dtype, int is_A, int op, size_t rows, size_t k, const void *X, size_t ld, double *amax, double *sumsq, void *stream);
+
+/* Shifts from (globally reduced) statistics: kind 0 = fast-mode shift (src/scaling_fast_real.hpp:6-14, stored negated),
+ * kind 1 = accurate-mode first shift s0 = 5 - ilogb(amax) (src/scaling_accu_real.hpp:39) */
+int g8_stage_shift_from_stats(const double *amax, const double *sumsq, size_t count, unsigned num_moduli, int kind, int16_t *sft, void *stream);
 
 /* Synthetic test matrices with the reference harness' generator (testing/make_matrix.hpp:33-82):
  * element idx <- curand_init(seed, idx, 0); phi < 0: standard normal, else (u-0.5)*exp(g*phi). */

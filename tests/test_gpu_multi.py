@@ -1,0 +1,84 @@
+"""K-sharded path on real GPUs (needs >= 2 devices; skipped otherwise): NCCL collectives + CUDA stage kernels.
+Accurate mode must equal the single-GPU g8_gemm on the concatenated operands bit for bit (both exchange variants)."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import gemmul8_b200 as g8
+        from gemmul8_b200 import multi_gpu
+
+        ok_all = True
+        for dtype, N in ((torch.float64, 14), (torch.float32, 6)):
+            m, n, kl = 300, 256, 384
+            K = kl * world
+            # full operands (same on every rank), column-major
+            A = g8.randmat(m, K, dtype, phi=0.5, seed=11, device=f"cuda:{rank}")
+            B = g8.randmat(K, n, dtype, phi=0.5, seed=22, device=f"cuda:{rank}")
+            Ar = A.view(K, m)[rank * kl:(rank + 1) * kl].contiguous().view(-1)            # columns K_r of A
+            Br = B.view(n, K)[:, rank * kl:(rank + 1) * kl].contiguous().view(-1)          # rows K_r of B
+            for fast in (False, True):
+                Cfull = torch.zeros(m * n, dtype=dtype, device=f"cuda:{rank}")
+                tot, _, _ = g8.work_size(m, n, K, N)
+                work = torch.empty(tot, dtype=torch.uint8, device=f"cuda:{rank}")
+                g8.gemm("N", "N", m, n, K, 1.0, A, m, B, K, 0.0, Cfull, m, N, fast, work)
+                for variant in ("int32", "residue"):
+                    plan = multi_gpu.KShardGemm(m, n, kl, N, fastmode=fast, dtype=dtype, device=f"cuda:{rank}", variant=variant)
+                    C = torch.zeros(plan.local_out_elems, dtype=dtype, device=f"cuda:{rank}")
+                    plan.run(Ar, Br, C)
+                    torch.cuda.synchronize()
+                    nc = n // world
+                    want = Cfull.view(n, m)[rank * nc:(rank + 1) * nc].reshape(-1)
+                    if not fast:
+                        ok = torch.equal(C, want)          # accurate mode: bit-identical to the single-GPU call
+                    else:
+                        ok = bool(((C - want).abs().max() / want.abs().max()) < (1e-9 if dtype == torch.float64 else 1e-3))
+                    ok_all &= ok
+                    if not ok:
+                        print(f"rank {rank} mismatch dtype={dtype} fast={fast} variant={variant}", flush=True)
+        q.put((rank, ok_all))
+    except Exception:
+        q.put((rank, False))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_kshard_nccl_matches_single_gpu(cuda):
+    import torch
+    import torch.multiprocessing as mp
+
+    world = min(torch.cuda.device_count(), 2)
+    if world < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+    assert all(ok for _, ok in res), res
