@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--size", type=int, default=8192)
     ap.add_argument("--moduli", type=int, default=14)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mg-variant", default="int32", choices=["int32", "residue"])
+    ap.add_argument("--mg-variant", default="residue", choices=["int32", "residue"])
     return ap.parse_args()
 
 

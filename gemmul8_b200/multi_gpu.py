@@ -68,8 +68,8 @@ class CudaStages:
         api._check(self.lib.g8_stage_split(self.dt, int(is_A), op, rows, k, X.data_ptr(), ld, self.N, mode, sft.data_ptr(), planes.data_ptr(),
                                            plane_stride, self.N, self._s()), "split")
 
-    def gemm(self, epi, A_lo, strideA, B_lo, strideB, m, n, k_pad, units, out, out_stride, ldc):
-        api._check(self.lib.g8_stage_gemm(epi, 0, A_lo.data_ptr(), strideA, B_lo.data_ptr(), strideB, m, n, k_pad, units, 0, None, None,
+    def gemm(self, epi, A_lo, strideA, B_lo, strideB, m, n, k_pad, units, out, out_stride, ldc, first=0):
+        api._check(self.lib.g8_stage_gemm(epi, 0, A_lo.data_ptr(), strideA, B_lo.data_ptr(), strideB, m, n, k_pad, units, first, None, None,
                                           out.data_ptr(), out_stride, ldc, None, None, self._s()), "gemm")
 
     def maxabs(self, C, rows, cols, ld, rowmax, colmax):
@@ -78,11 +78,11 @@ class CudaStages:
     def finalize_shift(self, sft, cmax, count):
         api._check(self.lib.g8_stage_finalize_shift(sft.data_ptr(), cmax.data_ptr(), count, self.N, self._s()), "finalize_shift")
 
-    def requant(self, C_hi, rows, cols, in_ld, in_us, units, C_mid, out_ld, out_us):
-        api._check(self.lib.g8_stage_requant_i32(C_hi.data_ptr(), rows, cols, in_ld, in_us, units, 0, C_mid.data_ptr(), out_ld, out_us, self._s()), "requant")
+    def requant(self, C_hi, rows, cols, in_ld, in_us, units, C_mid, out_ld, out_us, first=0):
+        api._check(self.lib.g8_stage_requant_i32(C_hi.data_ptr(), rows, cols, in_ld, in_us, units, first, C_mid.data_ptr(), out_ld, out_us, self._s()), "requant")
 
-    def residue_sum(self, parts, nparts, part_stride, rows, cols, in_ld, in_us, units, C_mid, out_ld, out_us):
-        api._check(self.lib.g8_stage_residue_sum(parts.data_ptr(), nparts, part_stride, rows, cols, in_ld, in_us, units, 0, C_mid.data_ptr(),
+    def residue_sum(self, parts, nparts, part_stride, rows, cols, in_ld, in_us, units, C_mid, out_ld, out_us, first=0):
+        api._check(self.lib.g8_stage_residue_sum(parts.data_ptr(), nparts, part_stride, rows, cols, in_ld, in_us, units, first, C_mid.data_ptr(),
                                                  out_ld, out_us, self._s()), "residue_sum")
 
     def crt(self, C_mid, ldmid, plane_stride, m, n, C, ldc, sftA, sftB, alpha, beta):
@@ -97,18 +97,23 @@ def _is_gloo(group=None):
     return dist.get_backend(group) == "gloo"
 
 
-def reduce_scatter_sum(out, inp, group=None):
-    """out <- sum over ranks of inp[rank * out.numel() : (rank + 1) * out.numel()]"""
+class _Done:
+    def wait(self):
+        return None
+
+
+def reduce_scatter_sum(out, inp, group=None, async_op=False):
+    """out <- sum over ranks of inp[rank * out.numel() : (rank + 1) * out.numel()].  Returns a handle with .wait()."""
     if _is_gloo(group):
         tmp = inp.clone()
         dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
         r = dist.get_rank(group)
         out.copy_(tmp[r * out.numel():(r + 1) * out.numel()])
-    else:
-        dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group)
+        return _Done()
+    return dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group, async_op=async_op) or _Done()
 
 
-def all_to_all(out, inp, group=None):
+def all_to_all(out, inp, group=None, async_op=False):
     if _is_gloo(group):
         W = dist.get_world_size(group)
         gathered = [torch.empty_like(inp) for _ in range(W)]
@@ -116,8 +121,8 @@ def all_to_all(out, inp, group=None):
         r, c = dist.get_rank(group), out.numel() // W
         for j in range(W):
             out[j * c:(j + 1) * c].copy_(gathered[j][r * c:(r + 1) * c])
-    else:
-        dist.all_to_all_single(out, inp, group=group)
+        return _Done()
+    return dist.all_to_all_single(out, inp, group=group, async_op=async_op) or _Done()
 
 
 class KShardGemm:
@@ -125,8 +130,8 @@ class KShardGemm:
     (A_r: m x k_local column-major with ld = m; B_r: k_local x n column-major with ld = k_local).
     n must be a multiple of the world size (each rank reconstructs n / world columns)."""
 
-    def __init__(self, m, n, k_local, num_moduli, fastmode=False, dtype=torch.float64, device=None, variant="int32", stages=None,
-                 group=None):
+    def __init__(self, m, n, k_local, num_moduli, fastmode=False, dtype=torch.float64, device=None, variant="residue", stages=None,
+                 group=None, pipeline_groups=1):
         if dtype not in (torch.float32, torch.float64):
             raise NotImplementedError("K-sharded path: real S/D GEMM only")
         self.group = group
@@ -144,8 +149,13 @@ class KShardGemm:
         self.B_lo = st.empty(self.sizeB * N, torch.int8)
         self.sftA = st.zeros(self.m_pad, torch.int16)
         self.sftB = st.zeros(self.n_pad, torch.int16)
+        # the moduli can be processed in `pipeline_groups` batches so that the exchange of batch g overlaps the GEMMs of batch g+1.
+        # Measured on 2 x B200 (r01): no gain -- the persistent GEMM owns all 148 SMs, so NCCL's copy kernels only get SMs between
+        # launches -- hence the default of ONE batch = one collective per call.
+        G = max(1, min(pipeline_groups, N))
+        self.batches = [(i * N // G, (i + 1) * N // G - i * N // G) for i in range(G)]  # (first modulus, count)
         per = n * N * self.m_pad
-        self.part = st.empty(per, torch.int32 if variant == "int32" else torch.int8)      # [col][modulus][row]
+        self.part = st.empty(per, torch.int32 if variant == "int32" else torch.int8)      # per batch: [col][modulus in batch][row]
         self.recv = st.empty(per // self.W if variant == "int32" else per, self.part.dtype)  # my column slab (x world for residue)
         self.C_mid = st.empty(N * self.nc * self.m_pad, torch.int8)                         # [modulus][col][row]
         if not self.fast:
@@ -192,15 +202,34 @@ class KShardGemm:
         self._shifts(A, B)
         st.split(True, 0, m, k, A, m, 0, self.sftA, self.A_lo, self.sizeA)
         st.split(False, 0, n, k, B, k, 0, self.sftB, self.B_lo, self.sizeB)
-        mp, nc = self.m_pad, self.nc
-        if self.variant == "int32":
-            st.gemm(1, self.A_lo, self.sizeA, self.B_lo, self.sizeB, m, n, self.k_pad, N, self.part, mp, N * mp)
-            reduce_scatter_sum(self.recv, self.part, self.group)   # the single NCCL reduce of the INT32 partials
-            st.requant(self.recv, mp, nc, N * mp, mp, N, self.C_mid, mp, nc * mp)
-        else:
-            st.gemm(0, self.A_lo, self.sizeA, self.B_lo, self.sizeB, m, n, self.k_pad, N, self.part, mp, N * mp)
-            all_to_all(self.recv, self.part, self.group)
-            st.residue_sum(self.recv, self.W, nc * N * mp, mp, nc, N * mp, mp, N, self.C_mid, mp, nc * mp)
+        mp, nc, W = self.m_pad, self.nc, self.W
+        pending = []  # (handle, batch) whose exchange is in flight
+
+        def finish(h, u0, nu, recv):
+            h.wait()  # the compute stream waits for the collective of this batch
+            out = self.C_mid[u0 * nc * mp:]
+            if self.variant == "int32":
+                st.requant(recv, mp, nc, nu * mp, mp, nu, out, mp, nc * mp, first=u0)
+            else:
+                st.residue_sum(recv, W, nc * nu * mp, mp, nc, nu * mp, mp, nu, out, mp, nc * mp, first=u0)
+
+        for (u0, nu) in self.batches:
+            # batch buffers are carved from the big ones: send [n][nu][mp], receive slab [nc][nu][mp] (x W for the residue variant)
+            part = self.part[u0 * n * mp:(u0 + nu) * n * mp]
+            A_g, B_g = self.A_lo[u0 * self.sizeA:], self.B_lo[u0 * self.sizeB:]
+            if self.variant == "int32":
+                recv = self.recv[u0 * nc * mp:(u0 + nu) * nc * mp]
+                st.gemm(1, A_g, self.sizeA, B_g, self.sizeB, m, n, self.k_pad, nu, part, mp, nu * mp, first=u0)
+                h = reduce_scatter_sum(recv, part, self.group, async_op=True)   # ONE reduce of the INT32 partials per batch
+            else:
+                recv = self.recv[u0 * n * mp:(u0 + nu) * n * mp]
+                st.gemm(0, A_g, self.sizeA, B_g, self.sizeB, m, n, self.k_pad, nu, part, mp, nu * mp, first=u0)
+                h = all_to_all(recv, part, self.group, async_op=True)
+            if pending:
+                finish(*pending.pop(0))
+            pending.append((h, u0, nu, recv))
+        while pending:
+            finish(*pending.pop(0))
         r0 = self.rank * nc
         st.crt(self.C_mid, mp, nc * mp, m, nc, C, m, self.sftA, self.sftB[r0:r0 + nc], alpha, beta)
         return C

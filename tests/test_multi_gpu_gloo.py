@@ -77,14 +77,14 @@ class OracleStages:
         for i in range(self.N):
             pl[i * plane_stride:i * plane_stride + rows * k_pad] = res[i].reshape(-1)
 
-    def gemm(self, epi, A_lo, strideA, B_lo, strideB, m, n, k_pad, units, out, out_stride, ldc):
+    def gemm(self, epi, A_lo, strideA, B_lo, strideB, m, n, k_pad, units, out, out_stride, ldc, first=0):
         a, b, o = A_lo.numpy(), B_lo.numpy(), out.numpy()
         for u in range(units):
             Au = a[u * strideA:u * strideA + m * k_pad].reshape(m, k_pad).astype(np.int64)
             Bu = b[u * strideB:u * strideB + n * k_pad].reshape(n, k_pad).astype(np.int64)
             H = Au @ Bu.T
             if epi == 0:
-                p = self.mods[u]
+                p = self.mods[first + u]
                 r = np.mod(H, p)
                 H = np.where(r > p // 2, r - p, r)
             for c in range(n):
@@ -105,18 +105,18 @@ class OracleStages:
         r = np.mod(H, p)
         return np.where(r > p // 2, r - p, r).astype(np.int8)
 
-    def requant(self, C_hi, rows, cols, in_ld, in_us, units, C_mid, out_ld, out_us):
+    def requant(self, C_hi, rows, cols, in_ld, in_us, units, C_mid, out_ld, out_us, first=0):
         src, dst = C_hi.numpy().astype(np.int64), C_mid.numpy()
         for u in range(units):
             for c in range(cols):
-                dst[u * out_us + c * out_ld:u * out_us + c * out_ld + rows] = self._sym(src[u * in_us + c * in_ld:u * in_us + c * in_ld + rows], self.mods[u])
+                dst[u * out_us + c * out_ld:u * out_us + c * out_ld + rows] = self._sym(src[u * in_us + c * in_ld:u * in_us + c * in_ld + rows], self.mods[first + u])
 
-    def residue_sum(self, parts, nparts, part_stride, rows, cols, in_ld, in_us, units, C_mid, out_ld, out_us):
+    def residue_sum(self, parts, nparts, part_stride, rows, cols, in_ld, in_us, units, C_mid, out_ld, out_us, first=0):
         src, dst = parts.numpy().astype(np.int64), C_mid.numpy()
         for u in range(units):
             for c in range(cols):
                 acc = sum(src[q * part_stride + u * in_us + c * in_ld:q * part_stride + u * in_us + c * in_ld + rows] for q in range(nparts))
-                dst[u * out_us + c * out_ld:u * out_us + c * out_ld + rows] = self._sym(acc, self.mods[u])
+                dst[u * out_us + c * out_ld:u * out_us + c * out_ld + rows] = self._sym(acc, self.mods[first + u])
 
     def crt(self, C_mid, ldmid, plane_stride, m, n, C, ldc, sftA, sftB, alpha, beta):
         cm = C_mid.numpy().reshape(self.N, n, ldmid)
