@@ -138,16 +138,18 @@ class Layout:
     mid_bytes: int
 
 
-def layout(m, n, k, num_moduli, is_complex=False, enable_skip_scalA=False, enable_skip_scalB=False) -> Layout:
+def layout(m, n, k, num_moduli, is_complex=False, enable_skip_scalA=False, enable_skip_scalB=False, backend=Backend.INT8) -> Layout:
     k_pad, m_pad, n_pad = pad256(k), pad256(m), pad256(n)
     sizeA, sizeB, sizeC = k_pad * m_pad, k_pad * n, m_pad * n
     g = 3 if is_complex else 1
+    num_mat = T.num_mat("INT8" if int(backend) == 0 else "FP8", num_moduli)  # planes per operand group
     a_lo = 0
-    sftA = a_lo + sizeA * (num_moduli + int(enable_skip_scalA)) * g
+    sftA = a_lo + sizeA * (num_mat + int(enable_skip_scalA)) * g
     b_lo = sftA + 2 * m_pad
-    sftB = b_lo + sizeB * (num_moduli + int(enable_skip_scalB)) * g
+    sftB = b_lo + sizeB * (num_mat + int(enable_skip_scalB)) * g
     c_mid = sftB + 2 * n_pad
-    return Layout(k_pad, m_pad, n_pad, sizeA, sizeB, sizeC, g, a_lo, sftA, b_lo, sftB, c_mid, 2 if is_complex else 1)
+    mid = (1 if int(backend) == 0 else 2) * (2 if is_complex else 1)
+    return Layout(k_pad, m_pad, n_pad, sizeA, sizeB, sizeC, g, a_lo, sftA, b_lo, sftB, c_mid, mid)
 
 
 def aligned_view(work: torch.Tensor) -> torch.Tensor:

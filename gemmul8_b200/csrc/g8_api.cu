@@ -79,8 +79,9 @@ static bool device_ok() {
 }
 
 static SplitArgs split_args(int is_A, int op, size_t rows, size_t k, const void *X, size_t ld, unsigned N, int16_t *sft,
-                            int8_t *base, size_t plane_stride, size_t group_stride_planes) {
+                            int8_t *base, size_t plane_stride, size_t group_stride_planes, int backend = INT8) {
     SplitArgs a{};
+    a.backend = backend;
     a.X = X, a.ld = ld, a.rows = rows, a.inner = k, a.k_pad = pad256(k), a.sft = sft;
     for (int g = 0; g < 3; ++g) a.planes[g] = base + g * group_stride_planes * plane_stride;
     a.plane_stride = plane_stride;
@@ -95,7 +96,8 @@ static int gemm_impl(const g8_gemm_desc &d, double *phase_ns) {
     if (!d.A || !d.B || !d.C || !d.alpha || !d.beta || !d.work) return G8_STATUS_INVALID_VALUE;
     if (d.dtype < F32 || d.dtype > C64 || d.op_A < 0 || d.op_A > 2 || d.op_B < 0 || d.op_B > 2) return G8_STATUS_INVALID_VALUE;
     if (d.num_moduli < 2 || d.num_moduli > G8_MAX_MODULI) return G8_STATUS_INVALID_VALUE;
-    if (d.backend != INT8) return G8_STATUS_NOT_SUPPORTED;
+    if (d.backend != INT8 && d.backend != FP8) return G8_STATUS_INVALID_VALUE;
+    if (d.backend == FP8 && d.dtype >= C32) return G8_STATUS_NOT_SUPPORTED; // complex FP8 (9 GEMMs per modulus) is not built yet
     if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
     if (d.m == 0 || d.n == 0) return 0;
 
@@ -133,8 +135,8 @@ static int gemm_impl(const g8_gemm_desc &d, double *phase_ns) {
         cudaMemsetAsync(sftA, 0, sizeof(int16_t) * s.m_pad, st);
         cudaMemsetAsync(sftB, 0, sizeof(int16_t) * s.n_pad, st);
     } else if (!(skipA && skipB)) {
-        SplitArgs sa = split_args(1, d.op_A, d.m, d.k, d.A, d.lda, N, sftA, A_lo, s.sizeA, groupA_planes);
-        SplitArgs sb = split_args(0, d.op_B, d.n, d.k, d.B, d.ldb, N, sftB, B_lo, s.sizeB, groupB_planes);
+        SplitArgs sa = split_args(1, d.op_A, d.m, d.k, d.A, d.lda, N, sftA, A_lo, s.sizeA, groupA_planes, d.backend);
+        SplitArgs sb = split_args(0, d.op_B, d.n, d.k, d.B, d.ldb, N, sftB, B_lo, s.sizeB, groupB_planes, d.backend);
         if (d.fastmode) {
             if (!skipA) launch_split(sa, d.dtype, 1, st);
             if (!skipB) launch_split(sb, d.dtype, 1, st);
@@ -151,18 +153,19 @@ static int gemm_impl(const g8_gemm_desc &d, double *phase_ns) {
             g.A = A_bound, g.B = B_bound, g.strideA = s.sizeA, g.strideB = s.sizeB;
             g.m = d.m, g.n = d.n, g.m_pad = s.m_pad, g.k_pad = s.k_pad;
             g.num_units = 1, g.first_modulus = 0;
-            g.epi = cplx ? EPI_BOUND_MAX_CPLX : EPI_BOUND_MAX;
+            g.epi = d.backend == FP8 ? EPI_F8_BOUND : (cplx ? EPI_BOUND_MAX_CPLX : EPI_BOUND_MAX);
+            g.k_true = (int)d.k;
             g.groupA[0] = 0, g.groupA[1] = 1, g.groupA[2] = 2;
             g.groupB[0] = 0, g.groupB[1] = 1, g.groupB[2] = 2;
             if (!cplx) g.groupA[1] = g.groupA[2] = g.groupB[1] = g.groupB[2] = 0;
             g.ldc = s.m_pad, g.rowmax = rowmax, g.colmax = colmax;
             if (int e = launch_gemm_tc(g, st)) return e;
             if (!skipA) {
-                launch_finalize_accu_shift(sftA, rowmax, d.m, (int)N, st);
+                launch_finalize_accu_shift(sftA, rowmax, d.m, (int)N, st, d.backend);
                 launch_split(sa, d.dtype, 0, st);
             }
             if (!skipB) {
-                launch_finalize_accu_shift(sftB, colmax, d.n, (int)N, st);
+                launch_finalize_accu_shift(sftB, colmax, d.n, (int)N, st, d.backend);
                 launch_split(sb, d.dtype, 0, st);
             }
         }
@@ -175,7 +178,7 @@ static int gemm_impl(const g8_gemm_desc &d, double *phase_ns) {
         g.A = A_lo, g.B = B_lo, g.strideA = s.sizeA, g.strideB = s.sizeB;
         g.m = d.m, g.n = d.n, g.m_pad = s.m_pad, g.k_pad = s.k_pad;
         g.num_units = (int)N, g.first_modulus = 0;
-        g.epi = cplx ? EPI_MOD_I8_CPLX : EPI_MOD_I8;
+        g.epi = d.backend == FP8 ? EPI_F8_MOD : (cplx ? EPI_MOD_I8_CPLX : EPI_MOD_I8);
         for (int i = 0; i < 3; ++i) g.groupA[i] = cplx ? i * (int)groupA_planes : 0, g.groupB[i] = cplx ? i * (int)groupB_planes : 0;
         g.out = C_mid, g.out_stride = s.sizeC, g.ldc = s.m_pad;
         if (int e = launch_gemm_tc(g, st)) return e;
@@ -186,6 +189,7 @@ static int gemm_impl(const g8_gemm_desc &d, double *phase_ns) {
     CrtArgs c{};
     c.C_mid = C_mid, c.ldmid = s.m_pad, c.plane_stride = s.sizeC, c.m = d.m, c.n = d.n, c.num_moduli = (int)N;
     c.C = d.C, c.ldc = d.ldc, c.sftA = sftA, c.sftB = sftB, c.alpha = d.alpha, c.beta = d.beta;
+    c.backend = d.backend;
     if (int e = launch_crt(c, d.dtype, st)) return e;
     tm.mark(4);
     tm.finish(phase_ns);
@@ -279,12 +283,14 @@ __attribute__((visibility("default"))) int g8_stage_gemm(int epilogue, int use_s
                   size_t k_pad, int num_units, int first_modulus, const int *groupA, const int *groupB, void *out, size_t out_stride,
                   size_t ldc, int32_t *rowmax, int32_t *colmax, void *stream) {
     if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
-    if (!A_lo || !B_lo || k_pad % 256 || epilogue < 0 || epilogue > 4) return G8_STATUS_INVALID_VALUE;
+    if (!A_lo || !B_lo || k_pad % 256 || epilogue < 0 || epilogue > 7) return G8_STATUS_INVALID_VALUE;
     GemmArgs g{};
     g.A = A_lo, g.B = B_lo, g.strideA = strideA, g.strideB = strideB, g.m = m, g.n = n, g.m_pad = pad256(m), g.k_pad = k_pad;
     g.num_units = num_units, g.first_modulus = first_modulus, g.epi = epilogue;
     for (int i = 0; i < 3; ++i) g.groupA[i] = groupA ? groupA[i] : 0, g.groupB[i] = groupB ? groupB[i] : 0;
     g.out = out, g.out_stride = out_stride, g.ldc = ldc, g.rowmax = rowmax, g.colmax = colmax;
+    g.k_true = (int)k_pad;
+    if (use_simt && epilogue > 4) return G8_STATUS_NOT_SUPPORTED;
     return use_simt ? launch_gemm_simt(g, static_cast<cudaStream_t>(stream)) : launch_gemm_tc(g, static_cast<cudaStream_t>(stream));
 }
 

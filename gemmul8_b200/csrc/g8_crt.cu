@@ -38,7 +38,7 @@ constexpr int CRT_NV = 4; // residue bytes (= scalar outputs) per thread: one 32
                           // small per-thread state -> full occupancy hides the serial FMA chains
 
 // MODE: 0 C=AB, 1 C+=AB, 2 C=-AB, 3 C-=AB, 4 general (host scalars), 5 general (device scalars)
-template <typename T, bool DD, int MODE, bool VECIO>
+template <typename T, bool DD, int MODE, bool VECIO, int BE>
 __global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t groups, size_t total) {
     using TR           = CrtTraits<T>;
     using U            = typename TR::U;
@@ -55,36 +55,47 @@ __global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t 
     double hi[NV], lo[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) hi[j] = 0.0, lo[j] = 0.0;
-    const int8_t *src = reinterpret_cast<const int8_t *>(c.C_mid) + (col * c.ldmid + row) * (TR::cplx ? 2 : 1);
-    const size_t pstride = c.plane_stride * (TR::cplx ? 2 : 1);
-    const int tbl1 = N - 2, tbl2 = N - thresholds(INT8).P_is_double - 1;
-    constexpr double kOff = 4503599627370496.0 + 128.0;
+    constexpr int MIDB   = (BE == INT8) ? 1 : 2; // bytes per residue: int8 (INT8 backend) / int16 (FP8 backend)
+    const int8_t *src = reinterpret_cast<const int8_t *>(c.C_mid) + (col * c.ldmid + row) * (TR::cplx ? 2 : 1) * MIDB;
+    const size_t pstride = c.plane_stride * (TR::cplx ? 2 : 1) * MIDB;
+    const int tbl1 = N - 2, tbl2 = N - thresholds(BE).P_is_double - 1;
+    constexpr double kOff = 4503599627370496.0 + (BE == INT8 ? 128.0 : 32768.0);
 #pragma unroll 4
     for (int i = 0; i < N; ++i) {
-        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)i * pstride)) ^ 0x80808080u;
         double cd[NV];
+        if constexpr (BE == INT8) {
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)i * pstride)) ^ 0x80808080u;
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const uint32_t b = __byte_perm(w, 0u, 0x4440 + j);
-            cd[j]            = __dadd_rn(__hiloint2double(0x43300000, (int)b), -kOff);
+            for (int j = 0; j < NV; ++j) {
+                const uint32_t b = __byte_perm(w, 0u, 0x4440 + j);
+                cd[j]            = __dadd_rn(__hiloint2double(0x43300000, (int)b), -kOff);
+            }
+        } else {
+            uint2 w = __ldg(reinterpret_cast<const uint2 *>(src + (size_t)i * pstride));
+            w.x ^= 0x80008000u, w.y ^= 0x80008000u;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const uint32_t b = __byte_perm(j < 2 ? w.x : w.y, 0u, (j & 1) ? 0x4432 : 0x4410);
+                cd[j]            = __dadd_rn(__hiloint2double(0x43300000, (int)b), -kOff);
+            }
         }
         if constexpr (DD) {
-            const double wx = g8d_qPi2[INT8][tbl2][i][0], wy = g8d_qPi2[INT8][tbl2][i][1];
+            const double wx = g8d_qPi2[BE][tbl2][i][0], wy = g8d_qPi2[BE][tbl2][i][1];
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
                 hi[j] = fma(wx, cd[j], hi[j]);
                 lo[j] = fma(wy, cd[j], lo[j]);
             }
         } else {
-            const double wv = g8d_qPi1[INT8][tbl1][i];
+            const double wv = g8d_qPi1[BE][tbl1][i];
 #pragma unroll
             for (int j = 0; j < NV; ++j) hi[j] = fma(wv, cd[j], hi[j]);
         }
     }
 
     // ---- fold modulo P, cast, unscale ----
-    const double invP = g8d_invP[INT8][N - 2];
-    const double Px = g8d_P[INT8][N - 2][0], Py = g8d_P[INT8][N - 2][1];
+    const double invP = g8d_invP[BE][N - 2];
+    const double Px = g8d_P[BE][N - 2][0], Py = g8d_P[BE][N - 2][1];
     const int sB = c.sftB[col];
     // sftA has pad256(m) entries, so the (unused) tail rows of the last group may be read safely; row % VEC == 0
     int16_t sA[VEC];
@@ -168,8 +179,13 @@ template <typename T, bool DD, int MODE> static void crt_go(const CrtArgs &c, co
     if (total == 0) return;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(c.C) % 16 == 0) && ((c.ldc * sizeof(T)) % 16 == 0);
     const unsigned grid = (unsigned)((total + 255) / 256);
-    if (vec_ok) crt_kernel<T, DD, MODE, true><<<grid, 256, 0, st>>>(c, hs, groups, total);
-    else crt_kernel<T, DD, MODE, false><<<grid, 256, 0, st>>>(c, hs, groups, total);
+    if (c.backend == FP8) {
+        if (vec_ok) crt_kernel<T, DD, MODE, true, FP8><<<grid, 256, 0, st>>>(c, hs, groups, total);
+        else crt_kernel<T, DD, MODE, false, FP8><<<grid, 256, 0, st>>>(c, hs, groups, total);
+    } else {
+        if (vec_ok) crt_kernel<T, DD, MODE, true, INT8><<<grid, 256, 0, st>>>(c, hs, groups, total);
+        else crt_kernel<T, DD, MODE, false, INT8><<<grid, 256, 0, st>>>(c, hs, groups, total);
+    }
 }
 
 template <typename T, bool DD> static void crt_mode(const CrtArgs &c, int mode, const Scalars &hs, cudaStream_t st) {
@@ -210,7 +226,7 @@ int launch_crt(const CrtArgs &c, int dtype, cudaStream_t st) {
             else if (hs.ar == -1.0 && hs.br == 1.0) mode = 3;
         }
     }
-    const bool dd = c.num_moduli > thresholds(INT8).P_is_double;
+    const bool dd = c.num_moduli > thresholds(c.backend).P_is_double;
     switch (dtype) {
     case F32: crt_mode<float, false>(c, mode, hs, st); break;
     case C32: crt_mode<float2, false>(c, mode, hs, st); break;

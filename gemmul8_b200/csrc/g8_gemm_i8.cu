@@ -75,6 +75,17 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// e4m3 x e4m3 -> f32 (kind::f8f6f4)
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -118,6 +129,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// kind::f8f6f4: c_format = F32 (1); a/b format = E4M3 (0); K-major both
+__host__ __device__ constexpr uint32_t make_idesc_f8(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 // ------------------------------------------------------------------------------------------------
 // kernel configuration
@@ -133,6 +148,10 @@ template <> struct EpiCfg<EPI_RAW_I32>        { static constexpr int TILE_COL = 
 template <> struct EpiCfg<EPI_BOUND_MAX>      { static constexpr int TILE_COL = 256, NACC = 1, NCHAIN = 1; };
 template <> struct EpiCfg<EPI_MOD_I8_CPLX>    { static constexpr int TILE_COL = 128, NACC = 3, NCHAIN = 1; };
 template <> struct EpiCfg<EPI_BOUND_MAX_CPLX> { static constexpr int TILE_COL = 128, NACC = 2, NCHAIN = 2; };
+template <> struct EpiCfg<EPI_F8_MOD>         { static constexpr int TILE_COL = 128, NACC = 3, NCHAIN = 1; };
+template <> struct EpiCfg<EPI_F8_BOUND>       { static constexpr int TILE_COL = 256, NACC = 1, NCHAIN = 1; };
+template <> struct EpiCfg<EPI_F8_RAW>         { static constexpr int TILE_COL = 256, NACC = 1, NCHAIN = 1; };
+template <int EPI> constexpr bool is_f8 = (EPI == EPI_F8_MOD || EPI == EPI_F8_BOUND || EPI == EPI_F8_RAW);
 
 template <int EPI> struct KernelShape {
     using C = EpiCfg<EPI>;
@@ -174,7 +193,11 @@ struct KParams {
     void *out;
     size_t out_stride, ldc;
     int32_t *rowmax, *colmax;
+    float inflate; // FP8 bound: (k + 1) * 2^-24
 };
+
+// FP8 plane bookkeeping (table.hpp:69-75): modulus idx owns planes [base, base + 2) (square moduli, idx < 6) or [base, base + 3)
+__host__ __device__ __forceinline__ int f8_plane_base(int idx) { return idx < 6 ? 2 * idx : 12 + 3 * (idx - 6); }
 
 // (acc, chain) -> (A group, B group)
 template <int EPI> __device__ __forceinline__ void chain_groups(int acc, int c, int &ga, int &gb) {
@@ -238,9 +261,18 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                 const TileCoord tc = tile_coord(t, P.tiles_l, P.tiles_c);
                 for (int acc = 0; acc < EC::NACC; ++acc)
                     for (int c = 0; c < EC::NCHAIN; ++c) {
-                        int ga, gb;
-                        chain_groups<EPI>(acc, c, ga, gb);
-                        const int planeA = P.groupA[ga] + tc.unit, planeB = P.groupB[gb] + tc.unit;
+                        int planeA, planeB;
+                        if constexpr (EPI == EPI_F8_MOD) {
+                            // square moduli: AhBl, AlBh, AlBl (gemmul8_real.hpp:159-170); otherwise Karatsuba hi*hi, lo*lo, sum*sum (:171-180)
+                            const int idx = P.first_modulus + tc.unit, base = f8_plane_base(idx);
+                            const bool sq = idx < 6;
+                            planeA = base + (sq ? (acc == 0 ? 0 : 1) : acc);
+                            planeB = base + (sq ? (acc == 1 ? 0 : 1) : acc);
+                        } else {
+                            int ga, gb;
+                            chain_groups<EPI>(acc, c, ga, gb);
+                            planeA = P.groupA[ga] + tc.unit, planeB = P.groupB[gb] + tc.unit;
+                        }
                         for (int kb = 0; kb < P.kblocks; ++kb) {
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             unsigned char *sL = smem + stage * KS::STAGE;
@@ -256,7 +288,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_i8(TILE_LANE, TILE_COL);
+            constexpr uint32_t idesc = is_f8<EPI> ? make_idesc_f8(TILE_LANE, TILE_COL) : make_idesc_i8(TILE_LANE, TILE_COL);
             int stage = 0, buf = 0;
             uint32_t phase = 0, tphase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -273,7 +305,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                             const uint64_t dL = make_smem_desc(sL), dC = make_smem_desc(sL + KS::STAGE_L);
 #pragma unroll
                             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                                umma_i8(d_tmem, dL + (uint64_t)(k * UMMA_K >> 4), dC + (uint64_t)(k * UMMA_K >> 4), idesc, accumulate);
+                                if constexpr (is_f8<EPI>) umma_f8(d_tmem, dL + (uint64_t)(k * UMMA_K >> 4), dC + (uint64_t)(k * UMMA_K >> 4), idesc, accumulate);
+                                else umma_i8(d_tmem, dL + (uint64_t)(k * UMMA_K >> 4), dC + (uint64_t)(k * UMMA_K >> 4), idesc, accumulate);
                                 accumulate = 1;
                             }
                             umma_commit(&empty_bar[stage]); // frees the smem slot once these MMAs retire
@@ -379,6 +412,72 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                         *reinterpret_cast<uint4 *>(dst + 2 * c0 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
                     }
                 }
+            } else if constexpr (EPI == EPI_F8_RAW) {
+                int32_t *dst = reinterpret_cast<int32_t *>(P.out) + (size_t)tc.unit * P.out_stride + (size_t)col_c * P.ldc + row0;
+#pragma unroll 1
+                for (int c0 = 0; c0 < TILE_COL; c0 += 32) {
+                    int32_t v[32];
+                    tmem_ld32(taddr0 + c0, v);
+                    tmem_ld_wait();
+                    if (col_ok) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<int4 *>(dst + c0 + 4 * j) = make_int4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                }
+            } else if constexpr (EPI == EPI_F8_BOUND) {
+                // find_max.hpp:82-96,166-188: max of fma_ru(ku, v, v); non-negative floats order like their bit patterns
+                int32_t cmax = 0;
+#pragma unroll 1
+                for (int c0 = 0; c0 < TILE_COL; c0 += 32) {
+                    int32_t v[32];
+                    tmem_ld32(taddr0 + c0, v);
+                    tmem_ld_wait();
+                    int32_t mine = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float f   = __int_as_float(v[j]);
+                        const int32_t x = __float_as_int(fmaxf(__fmaf_ru(P.inflate, f, f), 0.0f));
+                        cmax            = max(cmax, x);
+                        const int32_t r = __reduce_max_sync(0xffffffffu, x);
+                        mine            = (j == lane) ? r : mine;
+                    }
+                    if (mine > 0) atomicMax(&P.rowmax[row0 + c0 + lane], mine);
+                }
+                if (col_ok && cmax > 0) atomicMax(&P.colmax[col_c], cmax);
+            } else if constexpr (EPI == EPI_F8_MOD) {
+                // mod.hpp:106-130: c_j = float2int_rn(acc_j); square moduli: sqrt(p)*(c0 + c1) + c2, else 256*c0 + 16*(c2 - c0 - c1) + c1; mod p
+                const int32_t p = g8d_moduli[FP8][midx], pinv = g8d_pinv32[FP8][midx];
+                const bool sq   = midx < 6;
+                const int32_t sqrtp = sq ? g8d_f8sqrt[midx] : 0;
+                int16_t *dst = reinterpret_cast<int16_t *>(P.out) + (size_t)tc.unit * P.out_stride + (size_t)col_c * P.ldc + row0;
+#pragma unroll 1
+                for (int c0 = 0; c0 < TILE_COL; c0 += 16) {
+                    int32_t a0[16], a1[16], a2[16];
+                    tmem_ld16(taddr0 + c0, a0);
+                    tmem_ld16(taddr0 + TILE_COL + c0, a1);
+                    tmem_ld16(taddr0 + 2 * TILE_COL + c0, a2);
+                    tmem_ld_wait();
+                    uint32_t w[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        int32_t o[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int32_t c0i = __float2int_rn(__int_as_float(a0[2 * j + e]));
+                            const int32_t c1i = __float2int_rn(__int_as_float(a1[2 * j + e]));
+                            const int32_t c2i = __float2int_rn(__int_as_float(a2[2 * j + e]));
+                            const int32_t r0 = c0i - p * __mulhi(c0i, pinv), r1 = c1i - p * __mulhi(c1i, pinv), r2 = c2i - p * __mulhi(c2i, pinv);
+                            const int32_t t  = sq ? sqrtp * (r0 + r1) + r2 : (r0 * 256) + ((r2 - r0 - r1) * 16) + r1;
+                            o[e]             = mod_i32(t, p, pinv);
+                        }
+                        w[j] = (uint32_t)(o[0] & 0xFFFF) | ((uint32_t)o[1] << 16);
+                    }
+                    if (col_ok) {
+                        *reinterpret_cast<uint4 *>(dst + c0)     = make_uint4(w[0], w[1], w[2], w[3]);
+                        *reinterpret_cast<uint4 *>(dst + c0 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+                    }
+                }
             } else { // EPI_BOUND_MAX_CPLX
                 int32_t cmax = 0;
 #pragma unroll 1
@@ -467,6 +566,7 @@ template <int EPI> static int launch_tc(const GemmArgs &g, cudaStream_t st) {
     if (g.m == 0 || g.n == 0 || g.num_units == 0) return 0;
     int planes = g.num_units;
     for (int i = 0; i < 3; ++i) planes = max(planes, max(g.groupA[i], g.groupB[i]) + g.num_units);
+    if (EPI == EPI_F8_MOD) planes = f8_plane_base(g.first_modulus + g.num_units);
     CUtensorMap mapL, mapC;
     if (!make_plane_map(&mapL, g.B, g.k_pad, g.n, planes, g.strideB, TILE_LANE)) return (int)cudaErrorNotSupported;
     if (!make_plane_map(&mapC, g.A, g.k_pad, g.m, planes, g.strideA, KS::TILE_COL)) return (int)cudaErrorNotSupported;
@@ -481,6 +581,7 @@ template <int EPI> static int launch_tc(const GemmArgs &g, cudaStream_t st) {
     for (int i = 0; i < 3; ++i) P.groupA[i] = g.groupA[i], P.groupB[i] = g.groupB[i];
     P.out = g.out, P.out_stride = g.out_stride, P.ldc = g.ldc;
     P.rowmax = g.rowmax, P.colmax = g.colmax;
+    P.inflate = (float)(g.k_true + 1) * 0x1p-24f;
 
     static bool attr_set = false;
     if (!attr_set) {
@@ -501,6 +602,9 @@ int launch_gemm_tc(const GemmArgs &g, cudaStream_t st) {
     case EPI_BOUND_MAX: return launch_tc<EPI_BOUND_MAX>(g, st);
     case EPI_MOD_I8_CPLX: return launch_tc<EPI_MOD_I8_CPLX>(g, st);
     case EPI_BOUND_MAX_CPLX: return launch_tc<EPI_BOUND_MAX_CPLX>(g, st);
+    case EPI_F8_MOD: return launch_tc<EPI_F8_MOD>(g, st);
+    case EPI_F8_BOUND: return launch_tc<EPI_F8_BOUND>(g, st);
+    case EPI_F8_RAW: return launch_tc<EPI_F8_RAW>(g, st);
     }
     return (int)cudaErrorInvalidValue;
 }

@@ -17,9 +17,10 @@ struct SplitArgs {
     int num_moduli;
     int row_contig;      // 1: row r contiguous along inner; 0: element (r,l) at X[l*ld + r]
     int conj;            // complex only: conjugate on load (op == C)
+    int backend;         // INT8 (int8 residues) or FP8 (2-3 e4m3 pieces per residue, real types only)
 };
 void launch_split(const SplitArgs &a, int dtype, int mode, cudaStream_t st);
-void launch_finalize_accu_shift(int16_t *sft, const int32_t *cmax, size_t count, int num_moduli, cudaStream_t st);
+void launch_finalize_accu_shift(int16_t *sft, const int32_t *cmax, size_t count, int num_moduli, cudaStream_t st, int backend = INT8);
 // K-sharded multi-GPU support
 void launch_stats(const SplitArgs &a, int dtype, double *amax, double *sumsq, cudaStream_t st);
 void launch_shift_from_stats(const double *amax, const double *sumsq, size_t count, int num_moduli, int kind, int16_t *sft, cudaStream_t st);
@@ -34,6 +35,10 @@ enum GemmEpilogue : int {
     EPI_BOUND_MAX = 2, // rowmax[r] = max(rowmax[r], acc0), colmax[c] likewise                     (accurate, real)
     EPI_MOD_I8_CPLX   = 3, // C_mid[u] = {sym((acc0 - acc1) mod p), sym((acc2 - acc0 - acc1) mod p)}  (complex 3M)
     EPI_BOUND_MAX_CPLX = 4, // max over max(acc0, acc1) with acc0 = ArBr + AiBi, acc1 = ArBi + AiBr
+    // ---- FP8 (e4m3 x e4m3 -> f32, exact for the small-integer pieces) backend, real types ----
+    EPI_F8_MOD   = 5, // three products per modulus (square moduli: AhBl, AlBh, AlBl; else Karatsuba) -> int16 residue
+    EPI_F8_BOUND = 6, // bound product (one plane each), inflated by (k+1)*2^-24, row/col float maxima
+    EPI_F8_RAW   = 7, // TEST ONLY: raw f32 accumulator of one product per unit
 };
 
 struct GemmArgs {
@@ -48,7 +53,8 @@ struct GemmArgs {
     int epi;
     // complex: plane group offsets (in planes) of Re / Im / Re+Im inside A and B
     int groupA[3], groupB[3];
-    void *out;           // C_mid (int8 / int8x2) or C_hi (int32)
+    int k_true;          // FP8 bound epilogue: the unpadded k (error inflation factor)
+    void *out;           // C_mid (int8 / int8x2 / int16) or C_hi (int32 / f32)
     size_t out_stride;   // elements between output planes
     size_t ldc;          // leading dimension of the output (m_pad)
     int32_t *rowmax, *colmax;
@@ -69,6 +75,7 @@ struct CrtArgs {
     size_t ldc;
     const int16_t *sftA, *sftB;
     const void *alpha, *beta; // host or device pointers (resolved by the launcher)
+    int backend;              // INT8: int8 residues, FP8: int16 residues and the FP8 moduli tables
 };
 int launch_crt(const CrtArgs &c, int dtype, cudaStream_t st);
 

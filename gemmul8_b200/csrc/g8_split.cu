@@ -19,6 +19,9 @@
 // same shuffle tree.
 #include "g8_internal.cuh"
 
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+
 namespace g8 {
 
 // ------------------------------------------------------------------------------------------------
@@ -147,16 +150,21 @@ __device__ __forceinline__ double group_rem(double x, double M, double invM) {
     const double q = __dadd_rn(__fma_rn(x, invM, kMagic), -kMagic);
     return __fma_rn(-M, q, x);
 }
-template <bool LARGE> __device__ __forceinline__ double level1(double x, int g) {
-    const double M = g8d_grpM[g], invM = g8d_grpInvM[g];
-    if constexpr (LARGE) x = group_rem(x, M * 1048576.0, invM * (1.0 / 1048576.0));
+template <bool LARGE, int BE> __device__ __forceinline__ double level1(double x, int g) {
+    const double M = g8d_grpM[BE][g], invM = g8d_grpInvM[BE][g];
+    if constexpr (LARGE) x = group_rem(x, M * g8d_foldMul[BE][0], invM * g8d_foldMul[BE][1]);
     return group_rem(x, M, invM);
 }
 // symmetric residue (as int32; the low byte is the int8 plane value) of the level-1 remainder r modulo moduli[idx]
-__device__ __forceinline__ int32_t level2(double r, int idx) {
-    const int32_t a1  = __double2loint(__dadd_rn(r, g8d_mbias[idx]));
-    const uint32_t q  = __umulhi((uint32_t)a1, g8d_mmagic[idx]);
-    return (a1 - g8d_mhalf[idx]) - (int32_t)(q * (uint32_t)g8d_moduli[INT8][idx]);
+template <int BE> __device__ __forceinline__ int32_t level2(double r, int idx) {
+    const int32_t a1  = __double2loint(__dadd_rn(r, g8d_mbias[BE][idx]));
+    const uint32_t q  = __umulhi((uint32_t)a1, g8d_mmagic[BE][idx]);
+    return (a1 - g8d_mhalf[BE][idx]) - (int32_t)(q * (uint32_t)g8d_moduli[BE][idx]);
+}
+// x mod 1024, symmetric (FP8 modulus index 1; mod.hpp:79-93)
+__device__ __forceinline__ int32_t residue1024(double x) {
+    const int32_t v = __double2loint(__dadd_rn(group_rem(x, 4294967296.0, 1.0 / 4294967296.0), kMagic)) & 1023;
+    return v > 512 ? v - 1024 : v;
 }
 // x mod 256 (only the low byte is meaningful)
 __device__ __forceinline__ int32_t residue256(double x) {
@@ -208,8 +216,8 @@ __device__ __forceinline__ void split_store(const double (&xr)[NV], const double
         double rr[NV], ri[NV];
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            rr[j] = level1<LARGE>(xr[j], g);
-            if constexpr (CPLX) ri[j] = level1<LARGE>(xi[j], g);
+            rr[j] = level1<LARGE, INT8>(xr[j], g);
+            if constexpr (CPLX) ri[j] = level1<LARGE, INT8>(xi[j], g);
         }
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
@@ -222,8 +230,8 @@ __device__ __forceinline__ void split_store(const double (&xr)[NV], const double
                     int32_t a[4], b[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        a[j] = level2(rr[4 * q + j], idx);
-                        if constexpr (CPLX) b[j] = level2(ri[4 * q + j], idx);
+                        a[j] = level2<INT8>(rr[4 * q + j], idx);
+                        if constexpr (CPLX) b[j] = level2<INT8>(ri[4 * q + j], idx);
                     }
                     w0[q] = pack4(a[0], a[1], a[2], a[3]);
                     if constexpr (CPLX) {
@@ -238,13 +246,119 @@ __device__ __forceinline__ void split_store(const double (&xr)[NV], const double
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// FP8 backend (real types): every residue r (|r| <= p/2 <= 544) is written as 2 or 3 small integers that e4m3
+// represents exactly (mod.hpp:159-189): square moduli p = s^2: r = s*hi + lo, hi = rintf(r/s); other moduli:
+// r = 16*hi + lo with hi = sign(r)*ceil(|r|/16), plus the Karatsuba plane hi + lo.  Plane order as table.hpp:69-75.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fp8_of_int(int32_t v) { // |v| <= 16: exact in e4m3
+    return (uint32_t)__nv_cvt_float_to_fp8((float)v, __NV_SATFINITE, __NV_E4M3);
+}
+__device__ __forceinline__ uint32_t pack4u(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return a | (b << 8) | (c << 16) | (d << 24); }
+
+template <bool LARGE, int NV>
+__device__ __forceinline__ void split_store_f8(const double (&x)[NV], int num_moduli, int8_t *base, size_t plane_stride, size_t off) {
+    constexpr int NW = NV / 4;
+    auto store = [&](int plane, const uint32_t (&w)[NW]) {
+        int8_t *dst = base + (size_t)plane * plane_stride + off;
+        if constexpr (NW == 4) *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        else if constexpr (NW == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
+        else *reinterpret_cast<uint32_t *>(dst) = w[0];
+    };
+    auto emit = [&](int idx, const int32_t (&r)[NV]) {
+        const int pbase = idx < 6 ? 2 * idx : 12 + 3 * (idx - 6);
+        uint32_t hi[NV], lo[NV], sm[NV];
+        if (idx < 6) {
+            const float sq = (float)g8d_f8sqrt[idx], inv = __fdiv_rn(1.0f, sq);
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const float af = (float)r[j];
+                const float h  = rintf(__fmul_rn(af, inv));
+                const float l  = __fmaf_rn(-sq, h, af);
+                hi[j] = fp8_of_int((int32_t)h), lo[j] = fp8_of_int((int32_t)l);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const int32_t a = r[j], s = a >> 31;
+                const int32_t q = ((a ^ s) - s + 15) >> 4;   // ceil(|a| / 16)
+                const int32_t h = (q ^ s) - s;               // sign(a) * q
+                const int32_t l = a - 16 * h;
+                hi[j] = fp8_of_int(h), lo[j] = fp8_of_int(l), sm[j] = fp8_of_int(h + l);
+            }
+        }
+        uint32_t w[NW];
+#pragma unroll
+        for (int q = 0; q < NW; ++q) w[q] = pack4u(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+        store(pbase, w);
+#pragma unroll
+        for (int q = 0; q < NW; ++q) w[q] = pack4u(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+        store(pbase + 1, w);
+        if (idx >= 6) {
+#pragma unroll
+            for (int q = 0; q < NW; ++q) w[q] = pack4u(sm[4 * q], sm[4 * q + 1], sm[4 * q + 2], sm[4 * q + 3]);
+            store(pbase + 2, w);
+        }
+    };
+    if (num_moduli > 1) { // modulus index 1: p = 1024
+        int32_t r[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) r[j] = residue1024(x[j]);
+        emit(1, r);
+    }
+    const int ngroups = g8d_numGroups[FP8][num_moduli];
+    for (int g = 0; g < ngroups; ++g) {
+        double rr[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) rr[j] = level1<LARGE, FP8>(x[j], g);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int idx = g8d_grpMembers[FP8][g][t];
+            if (idx >= 0 && idx < num_moduli) {
+                int32_t r[NV];
+#pragma unroll
+                for (int j = 0; j < NV; ++j) r[j] = level2<FP8>(rr[j], idx);
+                emit(idx, r);
+            }
+        }
+    }
+}
+
+// accurate mode, FP8: round-up conversion of |a| * 2^s0 (< 2^8) to e4m3 (scaling.hpp:48-54,80-85)
+template <typename U> __device__ __forceinline__ uint32_t upper_bound_f8(U a, const double f1, const double f2) {
+    const double v = __dmul_rn(__dmul_rn(fabs((double)a), f1), f2); // exact scaling
+    uint32_t r;
+    if constexpr (sizeof(U) == 8) r = (uint32_t)__nv_cvt_double_to_fp8(v, __NV_SATFINITE, __NV_E4M3);
+    else r = (uint32_t)__nv_cvt_float_to_fp8((float)v, __NV_SATFINITE, __NV_E4M3);
+    const float back = __half2float(__half(__nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)r, __NV_E4M3)));
+    return r + (uint32_t)((double)back < v);
+}
+
 // NV consecutive inner indices of one row: either the accurate-mode bound plane(s) (MODE 2, sft = s0) or all residue planes
-template <typename T, int REGIME, int MODE, int NV>
+template <typename T, bool LARGE, int MODE, int NV, int BE>
 __device__ __forceinline__ void emit_elements(const T (&v)[NV], int sft, const SplitArgs &a, size_t off) {
     using U             = typename Scalar<T>::U;
     constexpr bool CPLX = Scalar<T>::cplx;
     constexpr int NW    = NV / 4;
-    if constexpr (MODE == 2) {
+    if constexpr (BE == FP8 && !CPLX) {
+        const RowScale scale = make_scale(sft);
+        if constexpr (MODE == 2) {
+            uint32_t w[NW];
+#pragma unroll
+            for (int q = 0; q < NW; ++q)
+                w[q] = pack4u(upper_bound_f8<U>(v[4 * q], scale.f1, scale.f2), upper_bound_f8<U>(v[4 * q + 1], scale.f1, scale.f2),
+                              upper_bound_f8<U>(v[4 * q + 2], scale.f1, scale.f2), upper_bound_f8<U>(v[4 * q + 3], scale.f1, scale.f2));
+            int8_t *dst = a.planes[0] + off;
+            if constexpr (NW == 4) *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+            else if constexpr (NW == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
+            else *reinterpret_cast<uint32_t *>(dst) = w[0];
+        } else {
+            double x[NV];
+#pragma unroll
+            for (int j = 0; j < NV; ++j) x[j] = scaled_trunc<U>(v[j], scale);
+            split_store_f8<LARGE, NV>(x, a.num_moduli, a.planes[0], a.plane_stride, off);
+        }
+    } else if constexpr (MODE == 2) {
         uint32_t wr[NW], wi[NW];
 #pragma unroll
         for (int q = 0; q < NW; ++q) {
@@ -273,7 +387,7 @@ __device__ __forceinline__ void emit_elements(const T (&v)[NV], int sft, const S
             if constexpr (CPLX) xr[j] = scaled_trunc<U>(v[j].x, scale), xi[j] = scaled_trunc<U>(v[j].y, scale);
             else xr[j] = scaled_trunc<U>(v[j], scale), xi[j] = 0.0;
         }
-        split_store<(REGIME == 2), NV, CPLX>(xr, xi, a.num_moduli, a.planes, a.plane_stride, off);
+        split_store<LARGE, NV, CPLX>(xr, xi, a.num_moduli, a.planes, a.plane_stride, off);
     }
 }
 
@@ -289,7 +403,7 @@ template <typename T> __device__ __forceinline__ T ldg_conj(const T *p, bool con
     return v;
 }
 
-template <typename T, int REGIME, int MODE>
+template <typename T, bool LARGE, int MODE, int BE>
 __global__ void __launch_bounds__(256) split_rowcontig_kernel(SplitArgs a) {
     using U       = typename Scalar<T>::U;
     const T *in   = reinterpret_cast<const T *>(a.X) + (size_t)blockIdx.x * a.ld;
@@ -333,10 +447,10 @@ __global__ void __launch_bounds__(256) split_rowcontig_kernel(SplitArgs a) {
         __syncthreads();
         amax = s_max[0];
         if constexpr (MODE == 1) {
-            sft = fast_shift(amax, s_sum[0], g8d_log2P[INT8][a.num_moduli]);
+            sft = fast_shift(amax, s_sum[0], g8d_log2P[BE][a.num_moduli]);
             if (threadIdx.x == 0) a.sft[row] = (int16_t)(-sft);
         } else {
-            sft = accu_s0(amax);
+            sft = accu_s0(amax) + (BE == FP8 ? 2 : 0); // maxUFP: 5 (INT8) / 7 (FP8), template_type.hpp:147
             if (threadIdx.x == 0) a.sft[row] = (int16_t)sft;
         }
     }
@@ -351,7 +465,7 @@ __global__ void __launch_bounds__(256) split_rowcontig_kernel(SplitArgs a) {
             if (l + j < k) v[j] = ldg_conj(in + l + j, a.conj);
             else v[j] = T{};
         }
-        emit_elements<T, REGIME, (MODE == 3 ? 2 : MODE), NV>(v, sft, a, row_off + l);
+        emit_elements<T, LARGE, (MODE == 3 ? 2 : MODE), NV, BE>(v, sft, a, row_off + l);
     }
 }
 
@@ -360,7 +474,7 @@ __global__ void __launch_bounds__(256) split_rowcontig_kernel(SplitArgs a) {
 // of row blockIdx.x*32 + x, then lane-transposes through shared memory and reduces over the 32 classes
 // (find_max.hpp:40-64, 306-341).  MODE 1: fast shift, MODE 2: accurate s0.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int MODE>
+template <typename T, int MODE, int BE>
 __global__ void __launch_bounds__(1024) stats_rowstrided_kernel(SplitArgs a) {
     using U = typename Scalar<T>::U;
     __shared__ U s_max[32][33], s_sum[32][33];
@@ -384,8 +498,8 @@ __global__ void __launch_bounds__(1024) stats_rowstrided_kernel(SplitArgs a) {
     if constexpr (MODE == 1) sum = warp_sum_ru(s_sum[x][y]);
     row = blockIdx.x * 32 + y;
     if (row < (int)a.rows && x == 0) {
-        if constexpr (MODE == 1) a.sft[row] = (int16_t)(-fast_shift(amax, sum, g8d_log2P[INT8][a.num_moduli]));
-        else a.sft[row] = (int16_t)accu_s0(amax);
+        if constexpr (MODE == 1) a.sft[row] = (int16_t)(-fast_shift(amax, sum, g8d_log2P[BE][a.num_moduli]));
+        else a.sft[row] = (int16_t)(accu_s0(amax) + (BE == FP8 ? 2 : 0));
     }
 }
 
@@ -396,7 +510,7 @@ __global__ void __launch_bounds__(1024) stats_rowstrided_kernel(SplitArgs a) {
 //            16-byte store per plane; 8 lanes cover a 128-byte line.
 // MODE 0: residues of trunc(x * 2^-sft); MODE 2: bound plane(s) with s0 = sft (as stored)
 // ------------------------------------------------------------------------------------------------
-template <typename T, int REGIME, int MODE>
+template <typename T, bool LARGE, int MODE, int BE>
 __global__ void __launch_bounds__(512) split_rowstrided_kernel(SplitArgs a) {
     constexpr int TL = 128, NV = 8;               // tile: 32 rows x 128 inner; 16 segments of 8 per row
     constexpr int SW = (sizeof(T) == 16) ? 0 : 1; // swizzle granularity that keeps both phases bank-conflict free
@@ -434,16 +548,17 @@ __global__ void __launch_bounds__(512) split_rowstrided_kernel(SplitArgs a) {
         const int ll = seg * NV + j;
         v[j]         = tile[ll * 32 + (rr ^ (seg << SW))];
     }
-    emit_elements<T, REGIME, MODE, NV>(v, sft, a, off);
+    emit_elements<T, LARGE, MODE, NV, BE>(v, sft, a, off);
 }
 
 // accurate mode, stage (iii): sft = -(s0 + floor(fmaf_rd(-0x1.000006p-1f, log2f(float(max)), log2P)))
 // (scaling_accu_real.hpp:6-11,157-159,202-204); max[] was filled by the bound GEMM's atomicMax epilogue.
-__global__ void finalize_accu_shift_kernel(int16_t *__restrict__ sft, const int32_t *__restrict__ cmax, int count, int num_moduli) {
+__global__ void finalize_accu_shift_kernel(int16_t *__restrict__ sft, const int32_t *__restrict__ cmax, int count, int num_moduli, int backend) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    const float log2amax = __log2f(__int2float_rn(cmax[i]));
-    const int g          = __float2int_rd(__fmaf_rd(-0x1.000006p-1f, log2amax, g8d_log2P[INT8][num_moduli]));
+    // INT8: integer maxima; FP8: the maxima are non-negative floats stored by their bit pattern (scaling_accu_real.hpp:13-18)
+    const float log2amax = __log2f(backend == INT8 ? __int2float_rn(cmax[i]) : __int_as_float(cmax[i]));
+    const int g          = __float2int_rd(__fmaf_rd(-0x1.000006p-1f, log2amax, g8d_log2P[backend][num_moduli]));
     int s                = sft[i];
     s += g;
     sft[i] = (int16_t)(-s);
@@ -452,54 +567,55 @@ __global__ void finalize_accu_shift_kernel(int16_t *__restrict__ sft, const int3
 // ------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
-static int regime_of(int num_moduli) {
-    const Thresholds t = thresholds(INT8);
-    return num_moduli <= t.S ? 0 : (num_moduli <= t.M ? 1 : 2);
-}
+// |x| can exceed 2^63 (two level-1 folds needed) once num_moduli passes the backend's M threshold (common.hpp:15-27)
+static bool is_large(int backend, int num_moduli) { return num_moduli > thresholds(backend).M; }
 
-template <typename T, int MODE> static void launch_rowcontig(const SplitArgs &a, int regime, cudaStream_t st) {
+template <typename T, int MODE, int BE> static void launch_rowcontig(const SplitArgs &a, bool large, cudaStream_t st) {
     const dim3 grid((unsigned)a.rows);
-    if (MODE >= 2 || regime == 0) split_rowcontig_kernel<T, 0, MODE><<<grid, 256, 0, st>>>(a);
-    else if (regime == 1) split_rowcontig_kernel<T, 1, MODE><<<grid, 256, 0, st>>>(a);
-    else split_rowcontig_kernel<T, 2, MODE><<<grid, 256, 0, st>>>(a);
+    if (MODE >= 2 || !large) split_rowcontig_kernel<T, false, MODE, BE><<<grid, 256, 0, st>>>(a);
+    else split_rowcontig_kernel<T, true, MODE, BE><<<grid, 256, 0, st>>>(a);
 }
 
-template <typename T, int MODE> static void launch_rowstrided(const SplitArgs &a, int regime, cudaStream_t st) {
+template <typename T, int MODE, int BE> static void launch_rowstrided(const SplitArgs &a, bool large, cudaStream_t st) {
     const dim3 grid((unsigned)((a.rows + 31) / 32), (unsigned)(a.k_pad / 128));
     const size_t smem = 128 * 32 * sizeof(T);
     auto go = [&](auto kern) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<grid, 512, smem, st>>>(a);
     };
-    if (MODE == 2 || regime == 0) go(split_rowstrided_kernel<T, 0, MODE>);
-    else if (regime == 1) go(split_rowstrided_kernel<T, 1, MODE>);
-    else go(split_rowstrided_kernel<T, 2, MODE>);
+    if (MODE == 2 || !large) go(split_rowstrided_kernel<T, false, MODE, BE>);
+    else go(split_rowstrided_kernel<T, true, MODE, BE>);
 }
 
-template <typename T> static void split_typed(const SplitArgs &a, int mode, cudaStream_t st) {
-    const int regime = regime_of(a.num_moduli);
+template <typename T, int BE> static void split_typed(const SplitArgs &a, int mode, cudaStream_t st) {
+    const bool large = is_large(BE, a.num_moduli);
     if (a.row_contig) {
-        if (mode == 0) launch_rowcontig<T, 0>(a, regime, st);
-        else if (mode == 1) launch_rowcontig<T, 1>(a, regime, st);
-        else if (mode == 2) launch_rowcontig<T, 2>(a, regime, st);
-        else launch_rowcontig<T, 3>(a, regime, st);
+        if (mode == 0) launch_rowcontig<T, 0, BE>(a, large, st);
+        else if (mode == 1) launch_rowcontig<T, 1, BE>(a, large, st);
+        else if (mode == 2) launch_rowcontig<T, 2, BE>(a, large, st);
+        else launch_rowcontig<T, 3, BE>(a, large, st);
     } else {
         const dim3 sgrid((unsigned)((a.rows + 31) / 32)), sblock(32, 32);
-        if (mode == 1) stats_rowstrided_kernel<T, 1><<<sgrid, sblock, 0, st>>>(a);
-        if (mode == 2) stats_rowstrided_kernel<T, 2><<<sgrid, sblock, 0, st>>>(a);
-        if (mode >= 2) launch_rowstrided<T, 2>(a, regime, st);
-        else launch_rowstrided<T, 0>(a, regime, st);
+        if (mode == 1) stats_rowstrided_kernel<T, 1, BE><<<sgrid, sblock, 0, st>>>(a);
+        if (mode == 2) stats_rowstrided_kernel<T, 2, BE><<<sgrid, sblock, 0, st>>>(a);
+        if (mode >= 2) launch_rowstrided<T, 2, BE>(a, large, st);
+        else launch_rowstrided<T, 0, BE>(a, large, st);
     }
 }
 
 // mode 0: split with stored shifts, 1: fast (shift + split), 2: accurate stage (i) (s0 + bound planes),
 // 3: bound planes with the stored s0 (no statistics pass)
 void launch_split(const SplitArgs &a, int dtype, int mode, cudaStream_t st) {
+    if (a.backend == FP8) { // real types only (checked by the caller)
+        if (dtype == F32) split_typed<float, FP8>(a, mode, st);
+        else split_typed<double, FP8>(a, mode, st);
+        return;
+    }
     switch (dtype) {
-    case F32: split_typed<float>(a, mode, st); break;
-    case F64: split_typed<double>(a, mode, st); break;
-    case C32: split_typed<float2>(a, mode, st); break;
-    case C64: split_typed<double2>(a, mode, st); break;
+    case F32: split_typed<float, INT8>(a, mode, st); break;
+    case F64: split_typed<double, INT8>(a, mode, st); break;
+    case C32: split_typed<float2, INT8>(a, mode, st); break;
+    case C64: split_typed<double2, INT8>(a, mode, st); break;
     }
 }
 
@@ -580,8 +696,8 @@ void launch_shift_from_stats(const double *amax, const double *sumsq, size_t cou
     shift_from_stats_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(amax, sumsq, (int)count, num_moduli, kind, sft);
 }
 
-void launch_finalize_accu_shift(int16_t *sft, const int32_t *cmax, size_t count, int num_moduli, cudaStream_t st) {
-    finalize_accu_shift_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(sft, cmax, (int)count, num_moduli);
+void launch_finalize_accu_shift(int16_t *sft, const int32_t *cmax, size_t count, int num_moduli, cudaStream_t st, int backend) {
+    finalize_accu_shift_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(sft, cmax, (int)count, num_moduli, backend);
 }
 
 } // namespace g8

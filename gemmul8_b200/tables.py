@@ -166,23 +166,32 @@ def mod_pow2(backend: str):
 # `fast_mod_tables` proves the exact-floor condition a1 * (ceil(2^32/p) p - 2^32) < 2^32 for every modulus.
 # ---------------------------------------------------------------------------------------------
 MAGIC_RINT = 1.5 * 2.0 ** 52
-GROUP_SIZE = 3
 
 
 def fast_mod_tables(backend: str = "INT8"):
+    """Groups, group products and per-modulus level-2 constants.  INT8: p_0 = 256 is handled by byte extraction and the
+    other moduli form groups of three; FP8: p_1 = 1024 is handled by masking and the others form groups of two (products
+    must stay below 2^24 so that the level-1 remainder is an exact small integer)."""
     mods = moduli(backend)
-    assert backend == "INT8" and mods[0] == 256
-    groups = [list(range(1 + GROUP_SIZE * g, min(1 + GROUP_SIZE * (g + 1), len(mods)))) for g in range((len(mods) - 1 + GROUP_SIZE - 1) // GROUP_SIZE)]
+    pow2_idx = 0 if backend == "INT8" else 1
+    gsz = 3 if backend == "INT8" else 2
+    order = [i for i in range(len(mods)) if i != pow2_idx]
+    groups = [order[j:j + gsz] for j in range(0, len(order), gsz)]
     grpM, magic, half, bias = [], [0] * len(mods), [0] * len(mods), [0.0] * len(mods)
-    for members in groups:
-        # a short last group borrows the preceding moduli for its product so that x / M_g stays below 2^51
-        span = list(range(members[-1] - GROUP_SIZE + 1, members[-1] + 1))
+    for gi, members in enumerate(groups):
+        # a short last group borrows preceding moduli for its product so that x / M_g stays below 2^51
+        span = list(members)
+        j = order.index(members[0])
+        while len(span) < gsz:
+            j -= 1
+            span.insert(0, order[j])
         M = 1
         for i in span:
             M *= mods[i]
-        assert 2 ** 21 < M < 2 ** 24
+        assert 2 ** 13 < M < 2 ** 24
         grpM.append(M)
-        vmax = int(0.501 * M) + 2  # |level-1 remainder| <= (0.5 + 2^-9) M
+        # |level-1 remainder| <= (0.5 + eps) M with eps = |x / M| * 2^-52 <= 2^-6.6 (x < 2^63, M > 2^17.6): allow 0.52 M
+        vmax = int(0.52 * M) + 2
         for i in members:
             pm = mods[i]
             h = pm // 2
@@ -192,7 +201,13 @@ def fast_mod_tables(backend: str = "INT8"):
             a1max = vmax + h + K * pm
             assert 0 < e <= pm and a1max * e < (1 << 32) and a1max < 2 ** 31, (pm, e, a1max)
             magic[i], half[i], bias[i] = mg, h, MAGIC_RINT + h + K * pm
-    return dict(groups=groups, grpM=grpM, magic=magic, half=half, bias=bias)
+    members = [list(g) + [-1] * (gsz - len(g)) for g in groups]
+    # number of groups needed for the first n moduli
+    ngroups = [0] * (len(mods) + 1)
+    for n in range(len(mods) + 1):
+        ngroups[n] = sum(1 for g in groups if g[0] < n)
+    return dict(groups=groups, members=members, grpM=grpM, magic=magic, half=half, bias=bias, ngroups=ngroups,
+                fold=20 if backend == "INT8" else 30)
 
 
 def hexf(x: float) -> str:

@@ -394,3 +394,89 @@ void g8o_crt_c(const int8_t *C_mid, size_t ldmid, size_t strideC, size_t m, size
             }
         }
 }
+
+/* ---------------------------------------------------------------- FP8 backend (real types): 16-bit residues
+ * The FP8 backend (moduli up to 1089, table.hpp:34-53) keeps every residue as 2-3 small e4m3 integers whose products
+ * recombine to r_a * r_b mod p (mod.hpp:106-189); mathematically C_mid = sym( sum_l r_a r_b  mod p ) as int16.  The
+ * restatement therefore works on the residues directly. */
+void g8o_split16_d(const double *X, size_t ld, int trans, size_t rows, size_t inner, size_t k_pad, const int16_t *sft,
+                   const int32_t *moduli, int num_moduli, int16_t *planes, size_t plane_stride) {
+    for (int i = 0; i < num_moduli; ++i)
+        for (size_t r = 0; r < rows; ++r) {
+            int16_t *dst = planes + (size_t)i * plane_stride + r * k_pad;
+            for (size_t l = 0; l < k_pad; ++l)
+                dst[l] = (l < inner) ? (int16_t)trunc_scal_mod(elem_d(X, ld, trans, r, l), -(int)sft[r], moduli[i]) : 0;
+        }
+}
+void g8o_split16_f(const float *X, size_t ld, int trans, size_t rows, size_t inner, size_t k_pad, const int16_t *sft,
+                   const int32_t *moduli, int num_moduli, int16_t *planes, size_t plane_stride) {
+    for (int i = 0; i < num_moduli; ++i)
+        for (size_t r = 0; r < rows; ++r) {
+            int16_t *dst = planes + (size_t)i * plane_stride + r * k_pad;
+            for (size_t l = 0; l < k_pad; ++l)
+                dst[l] = (l < inner) ? (int16_t)trunc_scal_mod((double)elem_f(X, ld, trans, r, l), -(int)sft[r], moduli[i]) : 0;
+        }
+}
+void g8o_gemm_mod_i16(const int16_t *A_lo, size_t strideA, const int16_t *B_lo, size_t strideB, size_t m, size_t n,
+                      size_t k_pad, const int32_t *moduli, int num_moduli, int16_t *C_mid, size_t ldc, size_t strideC) {
+    for (int i = 0; i < num_moduli; ++i)
+        for (size_t c = 0; c < n; ++c)
+            for (size_t r = 0; r < m; ++r) {
+                const int16_t *a = A_lo + (size_t)i * strideA + r * k_pad;
+                const int16_t *b = B_lo + (size_t)i * strideB + c * k_pad;
+                int64_t acc      = 0;
+                for (size_t l = 0; l < k_pad; ++l) acc += (int32_t)a[l] * (int32_t)b[l];
+                C_mid[(size_t)i * strideC + c * ldc + r] = (int16_t)sym_mod_i64(acc, moduli[i]);
+            }
+}
+static double crt_value16(const int16_t *Cmid, size_t stride, int num_moduli, int use_dd, const double *qPi1,
+                          const double *qPi2, const double *P, double invP) {
+    if (!use_dd) {
+        double s = 0.0;
+        for (int i = 0; i < num_moduli; ++i) s = fma(qPi1[i], (double)Cmid[(size_t)i * stride], s);
+        double q = rint(invP * s);
+        return fma(P[0], q, s);
+    }
+    double hi = 0.0, lo = 0.0;
+    for (int i = 0; i < num_moduli; ++i) {
+        double c = (double)Cmid[(size_t)i * stride];
+        hi       = fma(qPi2[2 * i], c, hi);
+        lo       = fma(qPi2[2 * i + 1], c, lo);
+    }
+    double q = rint(invP * hi);
+    return fma(P[1], q, fma(P[0], q, hi) + lo);
+}
+void g8o_crt16_d(const int16_t *C_mid, size_t ldmid, size_t strideC, size_t m, size_t n, int num_moduli, int use_dd,
+                 const double *qPi1, const double *qPi2, const double *P, double invP, const int16_t *sftA,
+                 const int16_t *sftB, int mode, double alpha, double beta, double *C, size_t ldc) {
+    for (size_t c = 0; c < n; ++c)
+        for (size_t r = 0; r < m; ++r) {
+            double v  = crt_value16(C_mid + c * ldmid + r, strideC, num_moduli, use_dd, qPi1, qPi2, P, invP);
+            double AB = scalbn(v, (int)sftA[r] + (int)sftB[c]);
+            double *o = C + c * ldc + r;
+            switch (mode) {
+            case 0: *o = AB; break;
+            case 1: *o = *o + AB; break;
+            case 2: *o = -AB; break;
+            case 3: *o = *o - AB; break;
+            default: *o = fma(beta, *o, alpha * AB); break;
+            }
+        }
+}
+void g8o_crt16_f(const int16_t *C_mid, size_t ldmid, size_t strideC, size_t m, size_t n, int num_moduli,
+                 const double *qPi1, const double *P, double invP, const int16_t *sftA, const int16_t *sftB, int mode,
+                 float alpha, float beta, float *C, size_t ldc) {
+    for (size_t c = 0; c < n; ++c)
+        for (size_t r = 0; r < m; ++r) {
+            double v = crt_value16(C_mid + c * ldmid + r, strideC, num_moduli, 0, qPi1, NULL, P, invP);
+            float AB = scalbnf((float)v, (int)sftA[r] + (int)sftB[c]);
+            float *o = C + c * ldc + r;
+            switch (mode) {
+            case 0: *o = AB; break;
+            case 1: *o = *o + AB; break;
+            case 2: *o = -AB; break;
+            case 3: *o = *o - AB; break;
+            default: *o = fmaf(beta, *o, alpha * AB); break;
+            }
+        }
+}

@@ -157,6 +157,76 @@ def accurate_shifts(A: Operand, B: Operand, num_moduli: int, backend="INT8"):
     return sftA, sftB, ambA, ambB
 
 
+def e4m3_round_up(x: np.ndarray) -> np.ndarray:
+    """smallest e4m3 value >= x (x >= 0, x < 448), as float64 (scaling.hpp:48-54)"""
+    import torch
+
+    t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    q = t.to(torch.float8_e4m3fn)
+    back = q.to(torch.float32)
+    bits = q.view(torch.uint8).to(torch.int32) + (back.double() < torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))).to(torch.int32)
+    return bits.to(torch.uint8).view(torch.float8_e4m3fn).to(torch.float64).numpy()
+
+
+def accurate_shifts_fp8(A: Operand, B: Operand, num_moduli: int):
+    """FP8 accurate mode (scaling_accu_real.hpp with maxUFP = 7): the device accumulates the bound product in f32 and
+    inflates it by (k+1)*2^-24 (find_max.hpp:82-96); we bracket its maximum and flag rows whose floor() depends on it."""
+    L = lib()
+    log2P = np.float32(T.log2P("FP8", num_moduli))
+    k = A.inner
+
+    def s0_and_bar(O):
+        v = O.view.astype(np.float64)
+        amax = np.abs(v).max(axis=1) if O.inner else np.zeros(O.rows)
+        s0 = np.array([7 - ilogb_exact(float(a)) for a in amax], dtype=np.int16)
+        bar = e4m3_round_up(np.abs(v) * np.exp2(s0.astype(np.float64))[:, None])
+        return s0, bar
+
+    s0A, Abar = s0_and_bar(A)
+    s0B, Bbar = s0_and_bar(B)
+    Cbar = Abar @ Bbar.T  # exact enough in f64 (values < 2^8, k <= 2^16)
+    ku = (k + 1) * 2.0 ** -24
+
+    def fin(s0, mx):
+        out = np.zeros(len(s0), dtype=np.int16)
+        amb = np.zeros(len(s0), dtype=bool)
+        for i, (s, x) in enumerate(zip(s0, mx)):
+            if x <= 0:
+                amb[i] = True
+                continue
+            lo = float(np.float32(x * (1 - ku)))
+            hi = float(np.float32(x * (1 + ku) * (1 + 2 * ku)))
+            g_lo = int(np.floor(float(log2P) - float.fromhex("0x1.000006p-1") * np.log2(hi)))
+            g_hi = int(np.floor(float(log2P) - float.fromhex("0x1.000006p-1") * np.log2(lo)))
+            t = float(log2P) - float.fromhex("0x1.000006p-1") * np.log2(hi)
+            amb[i] = (g_lo != g_hi) or (t - np.floor(t) < 2 ** -10) or (np.floor(t) + 1 - t < 2 ** -10)
+            out[i] = np.int16(-(int(s) + g_lo))
+        return out, amb
+
+    sftA, ambA = fin(s0A, Cbar.max(axis=1, initial=0))
+    sftB, ambB = fin(s0B, Cbar.max(axis=0, initial=0))
+    return sftA, sftB, ambA, ambB
+
+
+def decode_fp8_planes(raw: np.ndarray, num_moduli: int):
+    """Device planes of the FP8 backend (uint8 e4m3 codes, [num_mat, rows, k_pad], order of table.hpp:69-75) -> int16 residues
+    [num_moduli, rows, k_pad]; also checks the Karatsuba plane hi + lo."""
+    import torch
+
+    val = torch.from_numpy(np.ascontiguousarray(raw).view(np.uint8)).view(torch.float8_e4m3fn).to(torch.float32).numpy().astype(np.int32)
+    out = np.zeros((num_moduli,) + raw.shape[1:], dtype=np.int16)
+    ok = True
+    for idx in range(num_moduli):
+        if idx < 6:
+            base, s = 2 * idx, T.FP8_SQRT_MODULI[idx]
+            out[idx] = s * val[base] + val[base + 1]
+        else:
+            base = 12 + 3 * (idx - 6)
+            out[idx] = 16 * val[base] + val[base + 1]
+            ok &= bool(np.array_equal(val[base + 2], val[base] + val[base + 1]))
+    return out, ok
+
+
 def fast_shifts(A: Operand, B: Operand, num_moduli: int, backend="INT8"):
     """Fast-mode shifts (scaling_fast_real.hpp:6-49) with a sequential round-up sum of squares."""
     L = lib()
@@ -193,6 +263,13 @@ def split(O: Operand, sft: np.ndarray, num_moduli: int, backend="INT8"):
     mod = np.array(T.moduli(backend)[:num_moduli], dtype=np.int32)
     sft = np.ascontiguousarray(sft, dtype=np.int16)
     out = []
+    if backend == "FP8":  # real types: int16 residues (the device stores each as 2-3 e4m3 pieces, see decode_fp8_planes)
+        pz = _real_parts(O.view)[0]
+        planes = np.zeros((num_moduli, O.rows, k_pad), dtype=np.int16)
+        fn = L.g8o_split16_f if pz.dtype == np.float32 else L.g8o_split16_d
+        fn(_p(pz), _sz(O.inner), 1, _sz(O.rows), _sz(O.inner), _sz(k_pad), _p(sft), _p(mod), int(num_moduli),
+           _p(planes), _sz(O.rows * k_pad))
+        return [planes]
     for pz in _real_parts(O.view):
         planes = np.zeros((num_moduli, O.rows, k_pad), dtype=np.int8)
         fn = L.g8o_split_f if pz.dtype == np.float32 else L.g8o_split_d
@@ -216,6 +293,11 @@ def gemm_mod(A_lo, B_lo, m: int, n: int, num_moduli: int, backend="INT8"):
     mod = np.array(T.moduli(backend)[:num_moduli], dtype=np.int32)
     m_pad = pad256(m)
     k_pad = A_lo[0].shape[2]
+    if backend == "FP8":
+        C = np.zeros((num_moduli, n, m_pad), dtype=np.int16)
+        L.g8o_gemm_mod_i16(_p(A_lo[0]), _sz(A_lo[0].shape[1] * k_pad), _p(B_lo[0]), _sz(B_lo[0].shape[1] * k_pad),
+                           _sz(m), _sz(n), _sz(k_pad), _p(mod), int(num_moduli), _p(C), _sz(m_pad), _sz(m_pad * n))
+        return C
     if len(A_lo) == 1:
         C = np.zeros((num_moduli, n, m_pad), dtype=np.int8)
         L.g8o_gemm_mod_i8(_p(A_lo[0]), _sz(A_lo[0].shape[1] * k_pad), _p(B_lo[0]), _sz(B_lo[0].shape[1] * k_pad),
@@ -260,6 +342,17 @@ def crt(C_mid, m, n, num_moduli, sftA, sftB, dtype, alpha=1.0, beta=0.0, C0=None
     sftB = np.ascontiguousarray(sftB, dtype=np.int16)
     mode = 4 if device_scalars else _mode(alpha, beta)
     ldc = C.strides[1] // C.itemsize
+    if backend == "FP8":
+        assert not cplx
+        if f32:
+            L.g8o_crt16_f(_p(C_mid), _sz(m_pad), _sz(m_pad * n), _sz(m), _sz(n), int(num_moduli), _p(q1), _p(P),
+                          ctypes.c_double(invP), _p(sftA), _p(sftB), mode, ctypes.c_float(alpha), ctypes.c_float(beta),
+                          _p(C), _sz(ldc))
+        else:
+            L.g8o_crt16_d(_p(C_mid), _sz(m_pad), _sz(m_pad * n), _sz(m), _sz(n), int(num_moduli), use_dd, _p(q1), _p(q2),
+                          _p(P), ctypes.c_double(invP), _p(sftA), _p(sftB), mode, ctypes.c_double(alpha),
+                          ctypes.c_double(beta), _p(C), _sz(ldc))
+        return C
     if not cplx:
         if f32:
             L.g8o_crt_f(_p(C_mid), _sz(m_pad), _sz(m_pad * n), _sz(m), _sz(n), int(num_moduli), _p(q1), _p(P),
@@ -290,8 +383,11 @@ def emulate(A, B, op_A="N", op_B="N", num_moduli=14, fastmode=False, alpha=1.0, 
     m, n = oa.rows, ob.rows
     ambA = ambB = None
     if sftA is None or sftB is None:
-        f = fast_shifts if fastmode else accurate_shifts
-        sA, sB, ambA, ambB = f(oa, ob, num_moduli, backend)
+        if backend == "FP8" and not fastmode:
+            sA, sB, ambA, ambB = accurate_shifts_fp8(oa, ob, num_moduli)
+        else:
+            f = fast_shifts if fastmode else accurate_shifts
+            sA, sB, ambA, ambB = f(oa, ob, num_moduli, backend)
         sftA = sA if sftA is None else sftA
         sftB = sB if sftB is None else sftB
     A_lo = split(oa, sftA, num_moduli, backend)

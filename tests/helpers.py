@@ -41,7 +41,7 @@ def rand_matrix(rng, shape, dtype, phi=0.5):
 
 
 def run_gemm(A, B, op_A="N", op_B="N", num_moduli=14, fastmode=False, alpha=1.0, beta=0.0, C0=None, lda=None, ldb=None,
-             ldc=None, device_scalars=False, return_work=False):
+             ldc=None, device_scalars=False, return_work=False, backend=0):
     """Run g8_gemm on numpy inputs. A, B are the STORED matrices. Returns C (m x n) [, dict of workspace pieces]."""
     dtype = np.result_type(A.dtype, B.dtype)
     m = A.shape[0] if op_A.upper() == "N" else A.shape[1]
@@ -52,27 +52,36 @@ def run_gemm(A, B, op_A="N", op_B="N", num_moduli=14, fastmode=False, alpha=1.0,
     C0 = np.zeros((m, n), dtype=dtype) if C0 is None else C0.astype(dtype)
     dC, ldc = to_dev_colmajor(C0, ldc)
     cplx = dtype.kind == "c"
-    tot, _, _ = g8.work_size(m, n, k, num_moduli, is_complex=cplx)
+    tot, _, _ = g8.work_size(m, n, k, num_moduli, is_complex=cplx, backend=backend)
     work = torch.zeros(tot, dtype=torch.uint8, device="cuda")
     tdt = NP2T[np.dtype(dtype)]
     if device_scalars:
         alpha_t = torch.tensor([alpha], dtype=tdt, device="cuda")
         beta_t = torch.tensor([beta], dtype=tdt, device="cuda")
-        g8.gemm(op_A, op_B, m, n, k, alpha_t, dA, lda, dB, ldb, beta_t, dC, ldc, num_moduli, fastmode, work)
+        g8.gemm(op_A, op_B, m, n, k, alpha_t, dA, lda, dB, ldb, beta_t, dC, ldc, num_moduli, fastmode, work, backend=backend)
     else:
-        g8.gemm(op_A, op_B, m, n, k, alpha, dA, lda, dB, ldb, beta, dC, ldc, num_moduli, fastmode, work)
+        g8.gemm(op_A, op_B, m, n, k, alpha, dA, lda, dB, ldb, beta, dC, ldc, num_moduli, fastmode, work, backend=backend)
     torch.cuda.synchronize()
     C = from_dev_colmajor(dC, m, n, ldc)
     if not return_work:
         return C
-    return C, read_workspace(work, m, n, k, num_moduli, cplx)
+    return C, read_workspace(work, m, n, k, num_moduli, cplx, backend=backend)
 
 
-def read_workspace(work, m, n, k, num_moduli, cplx, enable_skip_scalA=False, enable_skip_scalB=False):
+def read_workspace(work, m, n, k, num_moduli, cplx, enable_skip_scalA=False, enable_skip_scalB=False, backend=0):
     """Pull sftA/sftB, the residue planes and C_mid out of a (single-buffer) workspace."""
-    L = api.layout(m, n, k, num_moduli, cplx, enable_skip_scalA, enable_skip_scalB)
+    L = api.layout(m, n, k, num_moduli, cplx, enable_skip_scalA, enable_skip_scalB, backend=backend)
     w = api.aligned_view(work).cpu().numpy()
     N, G = num_moduli, L.groups
+    if backend == 1:  # FP8 backend (real): num_mat e4m3 planes per operand, int16 C_mid
+        from gemmul8_b200 import tables as T
+        nm = T.num_mat("FP8", N)
+        out = {"sftA": w[L.sftA:L.sftA + 2 * m].view(np.int16).copy(), "sftB": w[L.sftB:L.sftB + 2 * n].view(np.int16).copy()}
+        out["A_raw"] = w[L.A_lo:L.A_lo + L.sizeA * nm].reshape(nm, L.m_pad, L.k_pad)[:, :m].copy()
+        out["B_raw"] = w[L.B_lo:L.B_lo + L.sizeB * nm].reshape(nm, n, L.k_pad).copy()
+        out["C_mid"] = w[L.C_mid:L.C_mid + 2 * L.sizeC * N].view(np.int16).reshape(N, n, L.m_pad).copy()
+        out["layout"] = L
+        return out
     nA = num_moduli + int(enable_skip_scalA)
     nB = num_moduli + int(enable_skip_scalB)
     out = {}

@@ -255,6 +255,36 @@ def check_e2e():
                        f"planes={okp} cmid={okm} C={okc} sftbad=({badA},{badB}) relerr={err:.2e}")
 
 
+def check_fp8():
+    """FP8 backend (real types): planes decode to the oracle's residues, C_mid and C bit-exact given the device shifts"""
+    for dtype, N in ((np.float64, 13), (np.float64, 8), (np.float64, 4), (np.float64, 20), (np.float32, 6), (np.float64, 14)):
+        for fast in (False, True):
+            for opA, opB in (("N", "N"), ("T", "T")):
+                m, n, k = 150, 70, 333
+                A = H.rand_matrix(rng, H.stored_shape(opA, m, k), dtype)
+                B = H.rand_matrix(rng, H.stored_shape(opB, k, n), dtype)
+                C, W = H.run_gemm(A, B, opA, opB, N, fast, return_work=True, backend=1)
+                r = O.emulate(A, B, opA, opB, N, fast, sftA=W["sftA"], sftB=W["sftB"], backend="FP8")
+                Ad, okA = O.decode_fp8_planes(W["A_raw"], N)
+                Bd, okB = O.decode_fp8_planes(W["B_raw"], N)
+                okp = okA and okB and np.array_equal(Ad, r["A_lo"][0]) and np.array_equal(Bd, r["B_lo"][0])
+                okm = np.array_equal(W["C_mid"][:, :, :m], r["C_mid"][:, :, :m])
+                okc = H.bits_equal(C, r["C"])
+                r2 = O.emulate(A, B, opA, opB, N, fast, backend="FP8")
+                badA = int(np.sum((r2["sftA"] != W["sftA"]) & ~r2["ambA"]))
+                badB = int(np.sum((r2["sftB"] != W["sftB"]) & ~r2["ambB"]))
+                opx = {"N": A, "T": A.T}[opA].astype(np.float64) @ {"N": B, "T": B.T}[opB].astype(np.float64)
+                err = np.abs(C - opx).max() / np.abs(opx).max()
+                report(f"fp8 {np.dtype(dtype).name} N={N} fast={fast} {opA}{opB}", okp and okm and okc and badA == 0 and badB == 0,
+                       f"planes={okp} cmid={okm} C={okc} sftbad=({badA},{badB}) relerr={err:.2e}")
+                if not okp:
+                    d = np.argwhere(Ad != r["A_lo"][0])
+                    print("   A plane diffs", len(d), d[:3].tolist(), "B", int(np.sum(Bd != r["B_lo"][0])), "kara ok", okA, okB, flush=True)
+                    if len(d):
+                        i, rr, l = d[0]
+                        print("   dev", Ad[i, rr, l], "ora", r["A_lo"][0][i, rr, l], flush=True)
+
+
 def check_ref():
     so = ROOT / "oracle/_ref/libgemmul8_ref.so"
     R = ctypes.CDLL(str(so))
@@ -306,6 +336,8 @@ if __name__ == "__main__":
         check_gemm(False, [(128, 128, 256, 2), (70, 50, 300, 3), (300, 200, 1000, 14), (512, 384, 2048, 4)])
     if what in ("e2e", "all"):
         check_e2e()
+    if what in ("fp8", "all"):
+        check_fp8()
     if what in ("ref", "all"):
         check_ref()
     print("FAILED:" if FAILS else "ALL PASSED", FAILS[:20], flush=True)
