@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--mode", default="accu", choices=["accu", "fast"])
     ap.add_argument("--size", type=int, default=8192)
     ap.add_argument("--moduli", type=int, default=14)
+    ap.add_argument("--backend", default="int8", choices=["int8", "fp8"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mg-variant", default="residue", choices=["int32", "residue"])
     return ap.parse_args()
@@ -172,6 +173,7 @@ def main():
 
     S, N = args.size, args.moduli
     fast = args.mode == "fast"
+    be = 0 if args.backend == "int8" else 1
     m = n = S
     k_local = S                      # every rank owns a k-slab of S columns/rows: weak scaling in K (total K = S * world)
     k_total = S * (world if distributed else 1)
@@ -189,9 +191,9 @@ def main():
         except (FileNotFoundError, OSError) as e:
             print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref/libgemmul8_ref.so not loadable: {e}"}))
             return 0
-        tot = ref.L.ref_work_size(0, 0, m, n, k_local, N, 0, 0, None, None)
+        tot = ref.L.ref_work_size(0, be, m, n, k_local, N, 0, 0, None, None)
     else:
-        tot, _, _ = g8.work_size(m, n, k_local, N)
+        tot, _, _ = g8.work_size(m, n, k_local, N, backend=be)
     work = torch.empty(tot, dtype=torch.uint8, device=dev)
     one = (ctypes.c_double * 1)(1.0)
     zero = (ctypes.c_double * 1)(0.0)
@@ -204,14 +206,14 @@ def main():
 
     def step_device():
         if ref is not None:
-            code = ref.L.ref_gemm(1, 0, 1, 0, 0, m, n, k_local, ctypes.addressof(one), A.data_ptr(), m, B.data_ptr(), k_local,
+            code = ref.L.ref_gemm(1, be, 1, 0, 0, m, n, k_local, ctypes.addressof(one), A.data_ptr(), m, B.data_ptr(), k_local,
                                   ctypes.addressof(zero), C.data_ptr(), m, N, int(fast), work.data_ptr(), None, None, 0, 0, 0, 0,
                                   ctypes.c_void_p(stream.cuda_stream), None)
             assert code == 0, code
         elif mg is not None:
             mg.run(A, B, C)
         else:
-            g8.gemm("N", "N", m, n, k_local, 1.0, A, m, B, k_local, 0.0, C, m, N, fast, work)
+            g8.gemm("N", "N", m, n, k_local, 1.0, A, m, B, k_local, 0.0, C, m, N, fast, work, backend=be)
 
     # pinned host copies for the end-to-end leg
     hA = torch.empty(m * k_local, dtype=dt).pin_memory(); hA.copy_(A)
@@ -220,7 +222,7 @@ def main():
     hC = torch.empty(out_elems, dtype=dt).pin_memory()
 
     host_plan = None
-    if ref is None and mg is None:
+    if ref is None and mg is None and be == 0:
         host_plan = g8.HostGemm(m, n, k_local, dt, N, fast, "N", "N", chunk=1024, device=dev)
 
     def step_e2e():
@@ -274,7 +276,7 @@ def main():
     if ref is None and mg is None:
         ph = []
         for _ in range(max(3, min(args.steps, 10))):
-            ph.append(g8.gemm("N", "N", m, n, k_local, 1.0, A, m, B, k_local, 0.0, C, m, N, fast, work, timing=True))
+            ph.append(g8.gemm("N", "N", m, n, k_local, 1.0, A, m, B, k_local, 0.0, C, m, N, fast, work, timing=True, backend=be))
         phases = [statistics.mean(p[i] for p in ph) for i in range(4)]
         peaks = {}
         pk = ROOT / "MEASURED_PEAKS.json"
@@ -283,7 +285,8 @@ def main():
         bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
         which = "2 x measured bf16_tflops_sustained (MEASURED_PEAKS.json)" if peaks else "2 x fallback 1.4 PFLOP/s bf16 sustained"
         kp, mp = api.pad256(k_local), api.pad256(m)
-        units = N  # the fused launch covers all moduli; the bound GEMM of accurate mode is a separate, smaller launch in phase 0
+        # the fused launch covers all moduli (FP8: three products per modulus); the bound GEMM of accurate mode is a separate launch in phase 0
+        units = N if be == 0 else 3 * N
         ops = 2.0 * mp * n * kp * units
         t_gemm = phases[1] * 1e-9
         ach = ops / t_gemm * 1e-12
@@ -295,7 +298,7 @@ def main():
         tm = (ctypes.c_double * 4)()
         ph = []
         for _ in range(3):
-            ref.L.ref_gemm(1, 0, 1, 0, 0, m, n, k_local, ctypes.addressof(one), A.data_ptr(), m, B.data_ptr(), k_local, ctypes.addressof(zero),
+            ref.L.ref_gemm(1, be, 1, 0, 0, m, n, k_local, ctypes.addressof(one), A.data_ptr(), m, B.data_ptr(), k_local, ctypes.addressof(zero),
                            C.data_ptr(), m, N, int(fast), work.data_ptr(), None, None, 0, 0, 0, 0, ctypes.c_void_p(stream.cuda_stream), tm)
             ph.append(list(tm))
         phases = [statistics.mean(p[i] for p in ph) for i in range(4)]
@@ -311,7 +314,7 @@ def main():
         "value": round(value, 2), "unit": "TFLOPS", "n_gpus": n_gpus, "steps": args.steps, "warmup": warmup,
         "ms_per_step": round(ms_dev, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int8 tensor-core residues (s8 x s8 -> s32) + f64 CRT; emulates f64", "data": "synthetic",
-        "config": {"workload": f"DGEMM {m}x{n}x{k_total} INT8 num_moduli={N} fastmode={int(fast)} opN/opN alpha=1 beta=0"
+        "config": {"workload": f"DGEMM {m}x{n}x{k_total} {args.backend.upper()} num_moduli={N} fastmode={int(fast)} opN/opN alpha=1 beta=0"
                                + (f", K-sharded over {world} GPUs (k={k_local} per GPU), variant={args.mg_variant}" if distributed else ""),
                    "inputs": "curand normal (phi=-1), seeds 12345/54321 as testing/make_matrix.hpp",
                    "l2": "inputs (2 x 512 MiB) and residue planes (2.6 GiB) are larger than the 126 MB L2; no explicit flush",

@@ -19,6 +19,7 @@
 #include "g8_internal.cuh"
 
 #include <cuda.h> // CUtensorMap (types only; the encoder is fetched through the runtime, no -lcuda)
+#include <cstdlib>
 #include <mutex>
 
 namespace g8 {
@@ -85,6 +86,57 @@ __device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_
         "}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// ---- cta_group::2 (CTA pair) variants ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of `smem_addr` (a shared::cta address of THIS CTA) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of a pair into its OWN smem, completing on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_3d_2sm(void *smem_dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_i8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of all prior MMAs -> arrive on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
 }
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
@@ -153,15 +205,19 @@ template <> struct EpiCfg<EPI_F8_BOUND>       { static constexpr int TILE_COL = 
 template <> struct EpiCfg<EPI_F8_RAW>         { static constexpr int TILE_COL = 256, NACC = 1, NCHAIN = 1; };
 template <int EPI> constexpr bool is_f8 = (EPI == EPI_F8_MOD || EPI == EPI_F8_BOUND || EPI == EPI_F8_RAW);
 
-template <int EPI> struct KernelShape {
+// CG = 1: one CTA per tile (128 columns of C x TILE_COL rows).  CG = 2: a CTA pair (tcgen05 cta_group::2) shares a
+// 256-column tile; each CTA stages its own 128 columns' operand plus HALF of the row-side operand, which halves the
+// shared-memory traffic per MMA and deepens the TMA ring.
+template <int EPI, int CG = 1> struct KernelShape {
     using C = EpiCfg<EPI>;
     static constexpr int TILE_COL   = C::TILE_COL;                 // MMA N: rows of C per tile (TMEM columns)
-    static constexpr int STAGE_L    = TILE_LANE * BLOCK_K;         // bytes: lane-side operand (B_lo tile)
-    static constexpr int STAGE_C    = TILE_COL * BLOCK_K;          // bytes: column-side operand (A_lo tile)
+    static constexpr int STAGE_L    = TILE_LANE * BLOCK_K;         // bytes: lane-side operand (B_lo tile), per CTA
+    static constexpr int STAGE_C    = TILE_COL / CG * BLOCK_K;     // bytes: column-side operand (A_lo tile), per CTA
     static constexpr int STAGE      = STAGE_L + STAGE_C;
-    static constexpr int NUM_STAGES = (TILE_COL == 256) ? 4 : 6;
-    static constexpr int ACC_COLS   = C::NACC * TILE_COL;          // TMEM columns per buffer
-    static constexpr int NUM_BUF    = 512 / ACC_COLS >= 2 ? 2 : 1;
+    static constexpr int NUM_STAGES = (220 * 1024) / STAGE > 8 ? 8 : (220 * 1024) / STAGE;
+    // TMEM is a ring of accumulator SLOTS of TILE_COL columns; a tile takes NACC consecutive slots.  With more slots than
+    // NACC (2 vs 1, 4 vs 3) the MMAs of the next tile start while the epilogue still drains the previous one.
+    static constexpr int NUM_BUF    = 512 / TILE_COL;
     static constexpr int SMEM_BYTES = NUM_STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -211,12 +267,16 @@ template <int EPI> __device__ __forceinline__ void chain_groups(int acc, int c, 
     }
 }
 
-template <int EPI>
+template <int EPI, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUtensorMap mapC, const KParams P) {
-    using KS = KernelShape<EPI>;
+    using KS = KernelShape<EPI, CG>;
     using EC = EpiCfg<EPI>;
     constexpr int TILE_COL = KS::TILE_COL, NUM_STAGES = KS::NUM_STAGES, NUM_BUF = KS::NUM_BUF;
+    // CTA pair bookkeeping: rank 0 (leader) issues the MMAs and owns the "full" / "TMEM empty" barriers of the pair
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const bool leader   = rank == 0;
+    const int cid = blockIdx.x / CG, ncl = gridDim.x / CG; // tile-scheduler identity: one work stream per CTA (pair)
 
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -239,16 +299,22 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
         }
         for (int b = 0; b < NUM_BUF; ++b) {
             mbar_init(&tfull_bar[b], 1);
-            mbar_init(&tempty_bar[b], 4); // one arrive per epilogue warp
+            mbar_init(&tempty_bar[b], 4 * CG); // one arrive per epilogue warp (of both CTAs of a pair)
         }
         fence_barrier_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all(); // the peer's barriers must be initialised before any remote arrive / TMA completion
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -257,7 +323,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int t = cid; t < total_tiles; t += ncl) {
                 const TileCoord tc = tile_coord(t, P.tiles_l, P.tiles_c);
                 for (int acc = 0; acc < EC::NACC; ++acc)
                     for (int c = 0; c < EC::NCHAIN; ++c) {
@@ -277,9 +343,17 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             unsigned char *sL = smem + stage * KS::STAGE;
                             unsigned char *sC = sL + KS::STAGE_L;
-                            mbar_expect_tx(&full_bar[stage], KS::STAGE);
-                            tma_load_3d(sL, &mapL, &full_bar[stage], kb * BLOCK_K, tc.tl * TILE_LANE, planeB);
-                            tma_load_3d(sC, &mapC, &full_bar[stage], kb * BLOCK_K, tc.tc * TILE_COL, planeA);
+                            if constexpr (CG == 2) {
+                                // both CTAs load their share; all bytes complete on the leader's barrier
+                                if (leader) mbar_expect_tx(&full_bar[stage], KS::STAGE * 2);
+                                const uint32_t lbar = mapa(smem_u32(&full_bar[stage]), 0);
+                                tma_load_3d_2sm(sL, &mapL, lbar, kb * BLOCK_K, tc.tl * (TILE_LANE * 2) + (int)rank * TILE_LANE, planeB);
+                                tma_load_3d_2sm(sC, &mapC, lbar, kb * BLOCK_K, tc.tc * TILE_COL + (int)rank * (TILE_COL / 2), planeA);
+                            } else {
+                                mbar_expect_tx(&full_bar[stage], KS::STAGE);
+                                tma_load_3d(sL, &mapL, &full_bar[stage], kb * BLOCK_K, tc.tl * TILE_LANE, planeB);
+                                tma_load_3d(sC, &mapC, &full_bar[stage], kb * BLOCK_K, tc.tc * TILE_COL, planeA);
+                            }
                             if (++stage == NUM_STAGES) stage = 0, phase ^= 1;
                         }
                     }
@@ -287,15 +361,15 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = is_f8<EPI> ? make_idesc_f8(TILE_LANE, TILE_COL) : make_idesc_i8(TILE_LANE, TILE_COL);
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = is_f8<EPI> ? make_idesc_f8(TILE_LANE * CG, TILE_COL) : make_idesc_i8(TILE_LANE * CG, TILE_COL);
             int stage = 0, buf = 0;
             uint32_t phase = 0, tphase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                mbar_wait(&tempty_bar[buf], tphase ^ 1);
-                tc_fence_after();
+            for (int t = cid; t < total_tiles; t += ncl) {
                 for (int acc = 0; acc < EC::NACC; ++acc) {
-                    const uint32_t d_tmem = tmem_base + buf * KS::ACC_COLS + acc * TILE_COL;
+                    mbar_wait(&tempty_bar[buf], tphase ^ 1); // slot drained by the epilogue of an earlier tile
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * TILE_COL;
                     uint32_t accumulate   = 0;
                     for (int c = 0; c < EC::NCHAIN; ++c)
                         for (int kb = 0; kb < P.kblocks; ++kb) {
@@ -305,16 +379,26 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                             const uint64_t dL = make_smem_desc(sL), dC = make_smem_desc(sL + KS::STAGE_L);
 #pragma unroll
                             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                                if constexpr (is_f8<EPI>) umma_f8(d_tmem, dL + (uint64_t)(k * UMMA_K >> 4), dC + (uint64_t)(k * UMMA_K >> 4), idesc, accumulate);
-                                else umma_i8(d_tmem, dL + (uint64_t)(k * UMMA_K >> 4), dC + (uint64_t)(k * UMMA_K >> 4), idesc, accumulate);
+                                const uint64_t a = dL + (uint64_t)(k * UMMA_K >> 4), b = dC + (uint64_t)(k * UMMA_K >> 4);
+                                if constexpr (CG == 2) {
+                                    if constexpr (is_f8<EPI>) umma_f8_2sm(d_tmem, a, b, idesc, accumulate);
+                                    else umma_i8_2sm(d_tmem, a, b, idesc, accumulate);
+                                } else {
+                                    if constexpr (is_f8<EPI>) umma_f8(d_tmem, a, b, idesc, accumulate);
+                                    else umma_i8(d_tmem, a, b, idesc, accumulate);
+                                }
                                 accumulate = 1;
                             }
-                            umma_commit(&empty_bar[stage]); // frees the smem slot once these MMAs retire
+                            // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+                            if constexpr (CG == 2) umma_commit_2sm(&empty_bar[stage]);
+                            else umma_commit(&empty_bar[stage]);
                             if (++stage == NUM_STAGES) stage = 0, phase ^= 1;
                         }
+                    // this accumulator is complete
+                    if constexpr (CG == 2) umma_commit_2sm(&tfull_bar[buf]);
+                    else umma_commit(&tfull_bar[buf]);
+                    if (++buf == NUM_BUF) buf = 0, tphase ^= 1;
                 }
-                umma_commit(&tfull_bar[buf]); // accumulators of this tile complete
-                if (++buf == NUM_BUF) buf = 0, tphase ^= 1;
             }
         }
     } else {
@@ -322,12 +406,22 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
         const int q = warp & 3;
         int buf = 0;
         uint32_t tphase = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int t = cid; t < total_tiles; t += ncl) {
             const TileCoord tc = tile_coord(t, P.tiles_l, P.tiles_c);
-            mbar_wait(&tfull_bar[buf], tphase);
+            // the NACC accumulators of this tile sit in consecutive ring slots
+            uint32_t ta[3] = {0, 0, 0};
+            int sb = buf;
+            uint32_t sp = tphase;
+#pragma unroll
+            for (int a = 0; a < EC::NACC; ++a) {
+                mbar_wait(&tfull_bar[sb], sp);
+                ta[a] = tmem_base + ((uint32_t)(q * 32) << 16) + sb * TILE_COL;
+                if (++sb == NUM_BUF) sb = 0, sp ^= 1;
+            }
             tc_fence_after();
-            const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * KS::ACC_COLS;
-            const int col_c   = tc.tl * TILE_LANE + q * 32 + lane; // column of C owned by this thread
+            const uint32_t taddr0 = ta[0], ta1 = ta[1], ta2 = ta[2];
+            (void)ta1, (void)ta2;
+            const int col_c   = tc.tl * (TILE_LANE * CG) + (int)rank * TILE_LANE + q * 32 + lane; // column of C owned by this thread
             const int row0    = tc.tc * TILE_COL;                  // first row of C of this tile
             const bool col_ok = col_c < P.n;
             const int midx    = P.first_modulus + tc.unit;
@@ -389,8 +483,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                 for (int c0 = 0; c0 < TILE_COL; c0 += 16) {
                     int32_t a0[16], a1[16], a2[16];
                     tmem_ld16(taddr0 + c0, a0);
-                    tmem_ld16(taddr0 + TILE_COL + c0, a1);
-                    tmem_ld16(taddr0 + 2 * TILE_COL + c0, a2);
+                    tmem_ld16(ta1 + c0, a1);
+                    tmem_ld16(ta2 + c0, a2);
                     tmem_ld_wait();
                     uint32_t w[8];
 #pragma unroll
@@ -455,8 +549,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                 for (int c0 = 0; c0 < TILE_COL; c0 += 16) {
                     int32_t a0[16], a1[16], a2[16];
                     tmem_ld16(taddr0 + c0, a0);
-                    tmem_ld16(taddr0 + TILE_COL + c0, a1);
-                    tmem_ld16(taddr0 + 2 * TILE_COL + c0, a2);
+                    tmem_ld16(ta1 + c0, a1);
+                    tmem_ld16(ta2 + c0, a2);
                     tmem_ld_wait();
                     uint32_t w[8];
 #pragma unroll
@@ -484,7 +578,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                 for (int c0 = 0; c0 < TILE_COL; c0 += 32) {
                     int32_t v0[32], v1[32];
                     tmem_ld32(taddr0 + c0, v0);
-                    tmem_ld32(taddr0 + TILE_COL + c0, v1);
+                    tmem_ld32(ta1 + c0, v1);
                     tmem_ld_wait();
                     int32_t mine = 0;
 #pragma unroll
@@ -502,16 +596,24 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
             // all TMEM reads of this warp are complete (wait::ld above): hand the buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-            if (++buf == NUM_BUF) buf = 0, tphase ^= 1;
+#pragma unroll
+            for (int a = 0; a < EC::NACC; ++a) {
+                if (lane == 0) {
+                    if constexpr (CG == 2) mbar_arrive_cluster(mapa(smem_u32(&tempty_bar[buf]), 0)); // the MMA warp lives in the leader CTA
+                    else mbar_arrive(&tempty_bar[buf]);
+                }
+                if (++buf == NUM_BUF) buf = 0, tphase ^= 1;
+            }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all(); // neither CTA may exit (or free TMEM) while the pair's MMAs / remote arrives are in flight
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        if constexpr (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
@@ -561,18 +663,26 @@ static int num_sms() {
     return n;
 }
 
-template <int EPI> static int launch_tc(const GemmArgs &g, cudaStream_t st) {
-    using KS = KernelShape<EPI>;
-    if (g.m == 0 || g.n == 0 || g.num_units == 0) return 0;
+// G8_GEMM_CTA_GROUP=1 forces the single-CTA kernel (debugging / A-B comparisons); default is the CTA-pair kernel
+static int cta_group_pref() {
+    static int v = [] {
+        const char *e = getenv("G8_GEMM_CTA_GROUP");
+        return (e && e[0] == '1') ? 1 : 2;
+    }();
+    return v;
+}
+
+template <int EPI, int CG> static int launch_tc_cg(const GemmArgs &g, cudaStream_t st) {
+    using KS = KernelShape<EPI, CG>;
     int planes = g.num_units;
     for (int i = 0; i < 3; ++i) planes = max(planes, max(g.groupA[i], g.groupB[i]) + g.num_units);
     if (EPI == EPI_F8_MOD) planes = f8_plane_base(g.first_modulus + g.num_units);
     CUtensorMap mapL, mapC;
     if (!make_plane_map(&mapL, g.B, g.k_pad, g.n, planes, g.strideB, TILE_LANE)) return (int)cudaErrorNotSupported;
-    if (!make_plane_map(&mapC, g.A, g.k_pad, g.m, planes, g.strideA, KS::TILE_COL)) return (int)cudaErrorNotSupported;
+    if (!make_plane_map(&mapC, g.A, g.k_pad, g.m, planes, g.strideA, KS::TILE_COL / CG)) return (int)cudaErrorNotSupported;
 
     KParams P{};
-    P.tiles_l       = (int)((g.n + TILE_LANE - 1) / TILE_LANE);
+    P.tiles_l       = (int)((g.n + TILE_LANE * CG - 1) / (TILE_LANE * CG));
     P.tiles_c       = (int)((g.m + KS::TILE_COL - 1) / KS::TILE_COL);
     P.num_units     = g.num_units;
     P.first_modulus = g.first_modulus;
@@ -585,14 +695,24 @@ template <int EPI> static int launch_tc(const GemmArgs &g, cudaStream_t st) {
 
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_i8_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, KS::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gemm_i8_tc_kernel<EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, KS::SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
     const int total = P.num_units * P.tiles_l * P.tiles_c;
-    const int grid  = min(total, num_sms());
-    gemm_i8_tc_kernel<EPI><<<grid, NUM_THREADS, KS::SMEM_BYTES, st>>>(mapL, mapC, P);
-    return (int)cudaGetLastError();
+    const int grid  = CG * min(total, num_sms() / CG);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(NUM_THREADS), cfg.dynamicSmemBytes = KS::SMEM_BYTES, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, gemm_i8_tc_kernel<EPI, CG>, mapL, mapC, P);
+}
+
+template <int EPI> static int launch_tc(const GemmArgs &g, cudaStream_t st) {
+    if (g.m == 0 || g.n == 0 || g.num_units == 0) return 0;
+    return cta_group_pref() == 2 ? launch_tc_cg<EPI, 2>(g, st) : launch_tc_cg<EPI, 1>(g, st);
 }
 
 int launch_gemm_tc(const GemmArgs &g, cudaStream_t st) {
