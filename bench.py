@@ -47,44 +47,54 @@ def parse():
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock / power / throttle reasons sampled through NVML every ~4 ms from a thread while the timed region runs
+    (the nvidia-smi -lms loop of the profiling recipe gives only 1-2 samples for a 100 ms region)."""
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self._stop, self.th, self.h = index, [], threading.Event(), None, None
+        self.errors, self.last_error = 0, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _loop(self):
+        nv, h = self.nv, self.h
+        while not self._stop.is_set():
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(h)))
+            except Exception as e:  # keep sampling; report how many reads failed
+                self.errors += 1
+                self.last_error = repr(e)
+            time.sleep(0.004)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+        if self.h is not None:
+            self.th = threading.Thread(target=self._loop, daemon=True)
+            self.th.start()
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
+        if self.th is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        busy = [s for s in sm if s > 0.5 * max(sm)] or sm
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        self.th.join()
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap,
+                 "hw_power_brake": nv.nvmlClocksEventReasonHwPowerBrakeSlowdown}
+        sm = [float(r[0]) for r in self.rows]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": [], "samples": 0}
+        reasons = sorted(k for k, bit in names.items() if any(r[2] & bit for r in self.rows))
+        return {"sm_mhz": statistics.median(sm), "sm_min_mhz": min(sm), "sm_max_mhz": self.max_sm,
+                "power_w_median": round(statistics.median(r[1] for r in self.rows), 1),
+                "power_w_max": round(max(r[1] for r in self.rows), 1), "reasons": reasons, "samples": len(sm),
+                "read_errors": self.errors, "note": "NVML, 4 ms period, timed region only; NVML power is a ~1 s running average"}
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
@@ -241,10 +251,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, sampler=None):
         for _ in range(warmup):
             fn()
         barrier()
+        if sampler is not None:
+            sampler.start()  # clocks are sampled DURING the timed region only
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
@@ -259,10 +271,8 @@ def main():
         return ms / steps
 
     warmup = max(args.warmup, 3)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ms_dev = timed(step_device, args.steps, warmup)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_dev = timed(step_device, args.steps, warmup, sampler)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, max(2, min(args.steps, 5)), 1)
 

@@ -223,7 +223,10 @@ def check_crt():
                                         dsA.data_ptr(), dsB.data_ptr(), pa, pb, stream())
                 torch.cuda.synchronize()
                 out = H.from_dev_colmajor(dC, m, n, ldc)
-                ok = code == 0 and H.bits_equal(out, ref)
+                # float types with N > 13 overflow binary32 (the reference documents N <= 13 for FP32, include/gemmul8.hpp:29-30):
+                # inf - inf gives NaNs whose sign/payload bits are not part of any contract -> compare NaN positions, bits elsewhere
+                nan_o, nan_r = np.isnan(out), np.isnan(ref)
+                ok = code == 0 and np.array_equal(nan_o, nan_r) and H.bits_equal(np.where(nan_o, 0, out), np.where(nan_r, 0, ref))
                 report(f"crt {np.dtype(dtype).name} N={N} a={alpha} b={beta} dev={dev}", ok, "" if ok else H.first_diff(out, ref, "C"))
 
 
