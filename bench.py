@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--moduli", type=int, default=14)
     ap.add_argument("--backend", default="int8", choices=["int8", "fp8"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mg-variant", default="residue", choices=["int32", "residue"])
+    ap.add_argument("--mg-variant", default="fused", choices=["int32", "residue", "fused"])
     return ap.parse_args()
 
 
@@ -274,6 +274,8 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_dev = timed(step_device, args.steps, warmup, sampler)
     clocks = sampler.stop() if rank == 0 else None
+    if mg is not None and os.environ.get("G8_MG_TRACE") == "1" and rank == 0:
+        print("[mg trace]", [(n_, round(t_, 3)) for n_, t_ in mg.trace_report()], file=sys.stderr)
     ms_e2e = timed(step_e2e, max(2, min(args.steps, 5)), 1)
 
     flops = 2.0 * m * n * k_total

@@ -39,10 +39,19 @@ SYMBOLS = {
                               c_void_p]),
     "g8_stage_crt": (c_int, [c_int, c_void_p, c_size_t, c_size_t, c_size_t, c_size_t, c_uint, c_void_p, c_size_t, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p]),
+    "g8_stage_crt_parts": (c_int, [c_int, c_void_p, c_int, c_size_t, c_size_t, c_size_t, c_size_t, c_size_t, c_uint, c_void_p, c_size_t, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "g8_stage_requant_i32": (c_int, [c_void_p, c_size_t, c_size_t, c_size_t, c_size_t, c_int, c_int, c_void_p, c_size_t, c_size_t, c_void_p]),
     "g8_stage_residue_sum": (c_int, [c_void_p, c_int, c_size_t, c_size_t, c_size_t, c_size_t, c_size_t, c_int, c_int, c_void_p, c_size_t,
                                      c_size_t, c_void_p]),
     "g8_stage_maxabs_i32": (c_int, [c_void_p, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "g8_stage_maxabs_i32_parts": (c_int, [c_void_p, c_int, c_size_t, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "g8_stage_gemm_scatter": (c_int, [c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_size_t, c_int, c_int,
+                                      ctypes.POINTER(c_void_p), c_int, c_int, c_size_t, c_size_t, c_void_p]),
+    "g8_peer_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p), c_void_p]),
+    "g8_peer_open": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
+    "g8_peer_close": (c_int, [c_void_p]),
+    "g8_peer_free": (c_int, [c_void_p]),
     "g8_stage_stats": (c_int, [c_int, c_int, c_int, c_size_t, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "g8_stage_shift_from_stats": (c_int, [c_void_p, c_void_p, c_size_t, c_uint, c_int, c_void_p, c_void_p]),
     "g8_randmat": (c_int, [c_int, c_void_p, c_size_t, c_size_t, c_double, ctypes.c_ulonglong, c_void_p]),

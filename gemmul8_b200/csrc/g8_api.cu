@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 
 namespace g8 {
 
@@ -210,22 +211,34 @@ __global__ void requant_i32_kernel(const int32_t *__restrict__ C_hi, size_t rows
     *reinterpret_cast<uint32_t *>(C_mid + (size_t)u * out_unit_stride + col * out_ld + r4) =
         (uint32_t)(a & 0xFF) | ((uint32_t)(b & 0xFF) << 8) | ((uint32_t)(c & 0xFF) << 16) | ((uint32_t)e << 24);
 }
-// sum of `nparts` int8 residue arrays (one per K-shard, identical layout) reduced mod p again
-__global__ void residue_sum_kernel(const int8_t *__restrict__ parts, int nparts, size_t part_stride, size_t rows4, size_t cols, size_t in_ld,
-                                   size_t in_unit_stride, int first_modulus, int8_t *__restrict__ C_mid, size_t out_ld, size_t out_unit_stride) {
+// sum of `nparts` int8 residue arrays (one per K-shard, identical layout) reduced mod p again.  16 consecutive rows per thread:
+// one 128-bit load per part, bytes accumulated with dp4a against one-hot selectors (sign-extending add of byte j in ONE instruction).
+__global__ void __launch_bounds__(256) residue_sum_kernel(const int8_t *__restrict__ parts, int nparts, size_t part_stride, size_t rows16, size_t cols,
+                                                          size_t in_ld, size_t in_unit_stride, int first_modulus, int8_t *__restrict__ C_mid, size_t out_ld,
+                                                          size_t out_unit_stride) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows4 * cols) return;
-    const size_t col = i / rows4, r4 = (i - col * rows4) * 4;
+    if (i >= rows16 * cols) return;
+    const size_t col = i / rows16, r0 = (i - col * rows16) * 16;
     const int u     = blockIdx.y;
     const int32_t p = g8d_moduli[INT8][first_modulus + u], pinv = g8d_pinv32[INT8][first_modulus + u];
-    int32_t acc[4] = {0, 0, 0, 0};
+    int32_t acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0;
+    const int8_t *src = parts + (size_t)u * in_unit_stride + col * in_ld + r0;
     for (int q = 0; q < nparts; ++q) {
-        const char4 v = *reinterpret_cast<const char4 *>(parts + (size_t)q * part_stride + (size_t)u * in_unit_stride + col * in_ld + r4);
-        acc[0] += v.x, acc[1] += v.y, acc[2] += v.z, acc[3] += v.w;
+        const int4 v = __ldcs(reinterpret_cast<const int4 *>(src + (size_t)q * part_stride));
+        const int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = __dp4a(w[j >> 2], 1 << (8 * (j & 3)), acc[j]);
     }
-    const int32_t a = mod_i32(acc[0], p, pinv), b = mod_i32(acc[1], p, pinv), c = mod_i32(acc[2], p, pinv), e = mod_i32(acc[3], p, pinv);
-    *reinterpret_cast<uint32_t *>(C_mid + (size_t)u * out_unit_stride + col * out_ld + r4) =
-        (uint32_t)(a & 0xFF) | ((uint32_t)(b & 0xFF) << 8) | ((uint32_t)(c & 0xFF) << 16) | ((uint32_t)e << 24);
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int32_t a = mod_i32(acc[4 * j], p, pinv), b = mod_i32(acc[4 * j + 1], p, pinv), c = mod_i32(acc[4 * j + 2], p, pinv),
+                      e = mod_i32(acc[4 * j + 3], p, pinv);
+        o[j] = (uint32_t)(a & 0xFF) | ((uint32_t)(b & 0xFF) << 8) | ((uint32_t)(c & 0xFF) << 16) | ((uint32_t)e << 24);
+    }
+    *reinterpret_cast<uint4 *>(C_mid + (size_t)u * out_unit_stride + col * out_ld + r0) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 // row / column maxima of an int32 slab (the reduced bound product of accurate mode); one block per column
 __global__ void maxabs_i32_kernel(const int32_t *__restrict__ C, size_t rows, size_t ld, int32_t *__restrict__ rowmax, int32_t *__restrict__ colmax) {
@@ -235,6 +248,30 @@ __global__ void maxabs_i32_kernel(const int32_t *__restrict__ C, size_t rows, si
         const int32_t v = col[r];
         cm = max(cm, v);
         if (v > 0) atomicMax(&rowmax[r], v);
+    }
+    cm = __reduce_max_sync(0xffffffffu, cm);
+    if ((threadIdx.x & 31) == 0 && cm > 0) atomicMax(&colmax[blockIdx.x], cm);
+}
+
+// bound product of accurate mode, K-sharded: sum of `nparts` int32 slabs (one per K-shard, written by the fused GEMM -> scatter),
+// then row / column maxima of the sum
+__global__ void __launch_bounds__(256) maxabs_i32_parts_kernel(const int32_t *__restrict__ parts, int nparts, size_t part_stride, size_t rows, size_t ld,
+                                                               int32_t *__restrict__ rowmax, int32_t *__restrict__ colmax) {
+    const int32_t *col = parts + (size_t)blockIdx.x * ld;
+    int32_t cm = 0;
+    for (size_t r = (size_t)threadIdx.x * 4; r < rows; r += (size_t)blockDim.x * 4) { // ld and rows' padding are multiples of 4 (m_pad)
+        int4 v = make_int4(0, 0, 0, 0);
+        for (int q = 0; q < nparts; ++q) {
+            const int4 w = __ldcs(reinterpret_cast<const int4 *>(col + (size_t)q * part_stride + r));
+            v.x += w.x, v.y += w.y, v.z += w.z, v.w += w.w;
+        }
+        const int32_t e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (r + j < rows) {
+                cm = max(cm, e[j]);
+                if (e[j] > 0 && e[j] > *reinterpret_cast<volatile int32_t *>(&rowmax[r + j])) atomicMax(&rowmax[r + j], e[j]); // plain pre-check saves most atomics
+            }
     }
     cm = __reduce_max_sync(0xffffffffu, cm);
     if ((threadIdx.x & 31) == 0 && cm > 0) atomicMax(&colmax[blockIdx.x], cm);
@@ -304,6 +341,19 @@ __attribute__((visibility("default"))) int g8_stage_crt(int dtype, const void *C
     return launch_crt(c, dtype, static_cast<cudaStream_t>(stream));
 }
 
+__attribute__((visibility("default"))) int g8_stage_crt_parts(int dtype, const void *parts, int nparts, size_t part_stride, size_t ldmid, size_t plane_stride, size_t m, size_t n,
+                                                               unsigned num_moduli, void *C, size_t ldc, const int16_t *sftA, const int16_t *sftB, const void *alpha,
+                                                               const void *beta, void *stream) {
+    if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
+    if (!parts || !C || !sftA || !sftB || !alpha || !beta || num_moduli < 2 || num_moduli > G8_MAX_MODULI) return G8_STATUS_INVALID_VALUE;
+    if (nparts < 1 || nparts > 64 || part_stride % 4 || (dtype != F32 && dtype != F64)) return G8_STATUS_INVALID_VALUE;
+    CrtArgs c{};
+    c.C_mid = parts, c.ldmid = ldmid, c.plane_stride = plane_stride, c.m = m, c.n = n, c.num_moduli = (int)num_moduli;
+    c.C = C, c.ldc = ldc, c.sftA = sftA, c.sftB = sftB, c.alpha = alpha, c.beta = beta;
+    c.nparts = nparts, c.part_stride = part_stride;
+    return launch_crt(c, dtype, static_cast<cudaStream_t>(stream));
+}
+
 __attribute__((visibility("default"))) int g8_stage_requant_i32(const int32_t *C_hi, size_t rows, size_t cols, size_t in_ld, size_t in_unit_stride, int num_units,
                          int first_modulus, int8_t *C_mid, size_t out_ld, size_t out_unit_stride, void *stream) {
     if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
@@ -319,12 +369,13 @@ __attribute__((visibility("default"))) int g8_stage_requant_i32(const int32_t *C
 __attribute__((visibility("default"))) int g8_stage_residue_sum(const int8_t *parts, int nparts, size_t part_stride, size_t rows, size_t cols, size_t in_ld, size_t in_unit_stride,
                          int num_units, int first_modulus, int8_t *C_mid, size_t out_ld, size_t out_unit_stride, void *stream) {
     if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
-    if (!parts || !C_mid || nparts < 1 || nparts > 64 || rows % 4 || in_ld % 4 || out_ld % 4 || in_unit_stride % 4 || out_unit_stride % 4 || part_stride % 4)
+    if (!parts || !C_mid || nparts < 1 || nparts > 64 || rows % 16 || in_ld % 16 || out_ld % 16 || in_unit_stride % 16 || out_unit_stride % 16 ||
+        part_stride % 16 || reinterpret_cast<uintptr_t>(parts) % 16 || reinterpret_cast<uintptr_t>(C_mid) % 16)
         return G8_STATUS_INVALID_VALUE;
     if (rows == 0 || cols == 0 || num_units == 0) return 0;
-    const size_t r4 = rows / 4;
-    const dim3 grid((unsigned)((r4 * cols + 255) / 256), (unsigned)num_units);
-    residue_sum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(parts, nparts, part_stride, r4, cols, in_ld, in_unit_stride, first_modulus,
+    const size_t r16 = rows / 16;
+    const dim3 grid((unsigned)((r16 * cols + 255) / 256), (unsigned)num_units);
+    residue_sum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(parts, nparts, part_stride, r16, cols, in_ld, in_unit_stride, first_modulus,
                                                                             C_mid, out_ld, out_unit_stride);
     return (int)cudaGetLastError();
 }
@@ -336,6 +387,54 @@ __attribute__((visibility("default"))) int g8_stage_maxabs_i32(const int32_t *C,
     maxabs_i32_kernel<<<(unsigned)cols, 256, 0, static_cast<cudaStream_t>(stream)>>>(C, rows, ld, rowmax, colmax);
     return (int)cudaGetLastError();
 }
+
+__attribute__((visibility("default"))) int g8_stage_maxabs_i32_parts(const int32_t *parts, int nparts, size_t part_stride, size_t rows, size_t cols, size_t ld,
+                                                                      int32_t *rowmax, int32_t *colmax, void *stream) {
+    if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
+    if (!parts || !rowmax || !colmax || nparts < 1 || nparts > G8_MAX_PEERS || ld % 4 || part_stride % 4 || reinterpret_cast<uintptr_t>(parts) % 16)
+        return G8_STATUS_INVALID_VALUE;
+    if (rows == 0 || cols == 0) return 0;
+    maxabs_i32_parts_kernel<<<(unsigned)cols, 256, 0, static_cast<cudaStream_t>(stream)>>>(parts, nparts, part_stride, rows, ld, rowmax, colmax);
+    return (int)cudaGetLastError();
+}
+
+// ---- fused GEMM -> scatter over peer memory (K-sharded multi-GPU) ----
+__attribute__((visibility("default"))) int g8_stage_gemm_scatter(int epilogue, const int8_t *A_lo, size_t strideA, const int8_t *B_lo, size_t strideB, size_t m, size_t n,
+                                                                  size_t k_pad, int num_units, int first_modulus, void *const *peer_out, int world, int rank,
+                                                                  size_t out_stride, size_t ldc, void *stream) {
+    if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
+    if (!A_lo || !B_lo || !peer_out || k_pad % 256 || (epilogue != EPI_MOD_I8 && epilogue != EPI_RAW_I32)) return G8_STATUS_INVALID_VALUE;
+    if (world < 1 || world > G8_MAX_PEERS || rank < 0 || rank >= world || n % (size_t)world || (n / (size_t)world) % 256) return G8_STATUS_INVALID_VALUE;
+    GemmArgs g{};
+    g.A = A_lo, g.B = B_lo, g.strideA = strideA, g.strideB = strideB, g.m = m, g.n = n, g.m_pad = pad256(m), g.k_pad = k_pad;
+    g.num_units = num_units, g.first_modulus = first_modulus, g.epi = epilogue;
+    g.out = nullptr, g.out_stride = out_stride, g.ldc = ldc, g.k_true = (int)k_pad;
+    for (int i = 0; i < world; ++i) {
+        if (!peer_out[i]) return G8_STATUS_INVALID_VALUE;
+        g.peer_out[i] = peer_out[i];
+    }
+    g.owner_cols = n / (size_t)world, g.rank = rank, g.world = world;
+    return launch_gemm_tc(g, static_cast<cudaStream_t>(stream));
+}
+
+// ---- device buffers that can be mapped into the other ranks of the node (CUDA IPC) ----
+__attribute__((visibility("default"))) int g8_peer_alloc(size_t bytes, void **dptr, void *handle64) {
+    if (!dptr || !handle64 || bytes == 0) return G8_STATUS_INVALID_VALUE;
+    cudaError_t e = cudaMalloc(dptr, bytes);
+    if (e != cudaSuccess) return (int)e;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    e = cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t *>(handle64), *dptr);
+    if (e != cudaSuccess) cudaFree(*dptr), *dptr = nullptr;
+    return (int)e;
+}
+__attribute__((visibility("default"))) int g8_peer_open(const void *handle64, void **dptr) {
+    if (!dptr || !handle64) return G8_STATUS_INVALID_VALUE;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    return (int)cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess);
+}
+__attribute__((visibility("default"))) int g8_peer_close(void *dptr) { return dptr ? (int)cudaIpcCloseMemHandle(dptr) : 0; }
+__attribute__((visibility("default"))) int g8_peer_free(void *dptr) { return dptr ? (int)cudaFree(dptr) : 0; }
 
 __attribute__((visibility("default"))) int g8_stage_stats(int dtype, int is_A, int op, size_t rows, size_t k, const void *X, size_t ld, double *amax, double *sumsq, void *stream) {
     if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;

@@ -15,6 +15,7 @@
 #include <cstdint>
 
 #define G8_MAX_MODULI 20
+#define G8_MAX_PEERS 8 // GPUs of one NVSwitch box
 
 // ---- constant tables: one host copy (g8h_*) and one __constant__ copy (g8d_*) per translation unit
 #define G8_TQ static const

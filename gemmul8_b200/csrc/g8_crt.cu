@@ -64,7 +64,23 @@ __global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t 
     for (int i = 0; i < N; ++i) {
         double cd[NV];
         if constexpr (BE == INT8) {
-            const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)i * pstride)) ^ 0x80808080u;
+            uint32_t w;
+            if (c.nparts <= 1) {
+                w = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)i * pstride));
+            } else {
+                // K-sharded: add the per-shard residues byte-wise (dp4a against one-hot selectors sign-extends and adds in one
+                // instruction), reduce mod p_i again -- what g8_stage_residue_sum does, without the round trip through HBM
+                int32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                for (int q = 0; q < c.nparts; ++q) {
+                    const int x = (int)__ldcs(reinterpret_cast<const uint32_t *>(src + (size_t)i * pstride + (size_t)q * c.part_stride));
+                    a0 = __dp4a(x, 0x00000001, a0), a1 = __dp4a(x, 0x00000100, a1);
+                    a2 = __dp4a(x, 0x00010000, a2), a3 = __dp4a(x, 0x01000000, a3);
+                }
+                const int32_t p = g8d_moduli[INT8][i], pinv = g8d_pinv32[INT8][i];
+                a0 = mod_i32(a0, p, pinv), a1 = mod_i32(a1, p, pinv), a2 = mod_i32(a2, p, pinv), a3 = mod_i32(a3, p, pinv);
+                w = (uint32_t)(a0 & 0xFF) | ((uint32_t)(a1 & 0xFF) << 8) | ((uint32_t)(a2 & 0xFF) << 16) | ((uint32_t)a3 << 24);
+            }
+            w ^= 0x80808080u;
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
                 const uint32_t b = __byte_perm(w, 0u, 0x4440 + j);

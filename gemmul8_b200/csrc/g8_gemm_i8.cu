@@ -203,6 +203,11 @@ template <> struct EpiCfg<EPI_BOUND_MAX_CPLX> { static constexpr int TILE_COL = 
 template <> struct EpiCfg<EPI_F8_MOD>         { static constexpr int TILE_COL = 128, NACC = 3, NCHAIN = 1; };
 template <> struct EpiCfg<EPI_F8_BOUND>       { static constexpr int TILE_COL = 256, NACC = 1, NCHAIN = 1; };
 template <> struct EpiCfg<EPI_F8_RAW>         { static constexpr int TILE_COL = 256, NACC = 1, NCHAIN = 1; };
+template <> struct EpiCfg<EPI_MOD_I8_SCATTER> { static constexpr int TILE_COL = 256, NACC = 1, NCHAIN = 1; };
+template <> struct EpiCfg<EPI_RAW_I32_SCATTER> { static constexpr int TILE_COL = 256, NACC = 1, NCHAIN = 1; };
+// EPI_MOD_I8_SCATTER staging: per epilogue warp 32 columns x (128 rows + 16 B pad); the pad makes the 16-byte shared stores of
+// the 32 lanes (one column each) bank-conflict free: 144 B stride = 36 banks -> lane l starts at bank 4l mod 32
+constexpr int SCAT_ROWS = 128, SCAT_PITCH = SCAT_ROWS + 16, SCAT_WARP_BYTES = 32 * SCAT_PITCH, SCAT_BYTES = 4 * SCAT_WARP_BYTES;
 template <int EPI> constexpr bool is_f8 = (EPI == EPI_F8_MOD || EPI == EPI_F8_BOUND || EPI == EPI_F8_RAW);
 
 // CG = 1: one CTA per tile (128 columns of C x TILE_COL rows).  CG = 2: a CTA pair (tcgen05 cta_group::2) shares a
@@ -218,7 +223,7 @@ template <int EPI, int CG = 1> struct KernelShape {
     // TMEM is a ring of accumulator SLOTS of TILE_COL columns; a tile takes NACC consecutive slots.  With more slots than
     // NACC (2 vs 1, 4 vs 3) the MMAs of the next tile start while the epilogue still drains the previous one.
     static constexpr int NUM_BUF    = 512 / TILE_COL;
-    static constexpr int SMEM_BYTES = NUM_STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = NUM_STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + ((EPI == EPI_MOD_I8_SCATTER || EPI == EPI_RAW_I32_SCATTER) ? SCAT_BYTES : 0);
 };
 
 struct TileCoord {
@@ -227,7 +232,7 @@ struct TileCoord {
 
 // unit-major; inside a unit, bands of GROUP lane-tiles are swept along the column-tile direction so that
 // the CTAs running concurrently share a small set of operand panels in L2.
-__device__ __forceinline__ TileCoord tile_coord(int t, int tiles_l, int tiles_c) {
+__device__ __forceinline__ TileCoord tile_coord(int t, int tiles_l, int tiles_c, int tl_rot = 0) {
     constexpr int GROUP = 16;
     const int per_unit  = tiles_l * tiles_c;
     TileCoord r;
@@ -239,6 +244,8 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int tiles_l, int tiles_c)
     const int gl = min(GROUP, tiles_l - band * GROUP);
     r.tc         = idx / gl;
     r.tl         = band * GROUP + (idx - r.tc * gl);
+    r.tl += tl_rot;
+    if (r.tl >= tiles_l) r.tl -= tiles_l;
     return r;
 }
 
@@ -250,6 +257,11 @@ struct KParams {
     size_t out_stride, ldc;
     int32_t *rowmax, *colmax;
     float inflate; // FP8 bound: (k + 1) * 2^-24
+    // fused GEMM -> scatter of the K-sharded multi-GPU path: columns [o * owner_cols, (o + 1) * owner_cols) of the output go to
+    // peer_out[o] (a peer-mapped buffer of rank o, or our own), at column (c - o * owner_cols).  owner_cols == 0: plain output `out`.
+    void *peer_out[G8_MAX_PEERS];
+    int owner_cols;
+    int tl_rot; // rotation of the lane-tile sweep so that the ranks do not all target the same owner at the same time
 };
 
 // FP8 plane bookkeeping (table.hpp:69-75): modulus idx owns planes [base, base + 2) (square moduli, idx < 6) or [base, base + 3)
@@ -324,7 +336,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             for (int t = cid; t < total_tiles; t += ncl) {
-                const TileCoord tc = tile_coord(t, P.tiles_l, P.tiles_c);
+                const TileCoord tc = tile_coord(t, P.tiles_l, P.tiles_c, P.tl_rot);
                 for (int acc = 0; acc < EC::NACC; ++acc)
                     for (int c = 0; c < EC::NCHAIN; ++c) {
                         int planeA, planeB;
@@ -407,7 +419,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
         int buf = 0;
         uint32_t tphase = 0;
         for (int t = cid; t < total_tiles; t += ncl) {
-            const TileCoord tc = tile_coord(t, P.tiles_l, P.tiles_c);
+            const TileCoord tc = tile_coord(t, P.tiles_l, P.tiles_c, P.tl_rot);
             // the NACC accumulators of this tile sit in consecutive ring slots
             uint32_t ta[3] = {0, 0, 0};
             int sb = buf;
@@ -425,10 +437,18 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
             const int row0    = tc.tc * TILE_COL;                  // first row of C of this tile
             const bool col_ok = col_c < P.n;
             const int midx    = P.first_modulus + tc.unit;
+            // output base and column index inside it (peer scatter: the whole 256-column tile belongs to one owner)
+            char *out_base = static_cast<char *>(P.out);
+            int col_o      = col_c;
+            if (P.owner_cols) {
+                const int owner = (tc.tl * (TILE_LANE * CG)) / P.owner_cols;
+                out_base        = static_cast<char *>(P.peer_out[owner]);
+                col_o           = col_c - owner * P.owner_cols;
+            }
 
             if constexpr (EPI == EPI_MOD_I8) {
                 const int32_t p = g8d_moduli[INT8][midx], pinv = g8d_pinv32[INT8][midx];
-                int8_t *dst = reinterpret_cast<int8_t *>(P.out) + (size_t)tc.unit * P.out_stride + (size_t)col_c * P.ldc + row0;
+                int8_t *dst = reinterpret_cast<int8_t *>(out_base) + (size_t)tc.unit * P.out_stride + (size_t)col_o * P.ldc + row0;
 #pragma unroll 1
                 for (int c0 = 0; c0 < TILE_COL; c0 += 32) {
                     int32_t v[32];
@@ -446,8 +466,59 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                         *reinterpret_cast<uint4 *>(dst + c0 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
                     }
                 }
+            } else if constexpr (EPI == EPI_MOD_I8_SCATTER) {
+                // residues -> shared memory (this thread's column, 128 rows at a time) -> ONE 128-byte cp.async.bulk per thread into
+                // the owner's buffer: NVLink sees full 128-byte writes issued by the copy engine instead of 16-byte stores that
+                // stall the epilogue warps on remote latency.
+                const int32_t p = g8d_moduli[INT8][midx], pinv = g8d_pinv32[INT8][midx];
+                int8_t *dst = reinterpret_cast<int8_t *>(out_base) + (size_t)tc.unit * P.out_stride + (size_t)col_o * P.ldc + row0;
+                unsigned char *stg = smem + NUM_STAGES * KS::STAGE + 256 + (warp - 2) * SCAT_WARP_BYTES + lane * SCAT_PITCH;
+                const uint32_t stg_s = smem_u32(stg);
+#pragma unroll 1
+                for (int h0 = 0; h0 < TILE_COL; h0 += SCAT_ROWS) {
+                    // the copy engine must have finished READING this thread's staging row (previous half / previous tile)
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#pragma unroll 1
+                    for (int c0 = 0; c0 < SCAT_ROWS; c0 += 32) {
+                        int32_t v[32];
+                        tmem_ld32(taddr0 + h0 + c0, v);
+                        tmem_ld_wait();
+                        uint32_t w[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int32_t r0 = mod_i32(v[4 * j], p, pinv), r1 = mod_i32(v[4 * j + 1], p, pinv);
+                            const int32_t r2 = mod_i32(v[4 * j + 2], p, pinv), r3 = mod_i32(v[4 * j + 3], p, pinv);
+                            w[j] = (uint32_t)(r0 & 0xFF) | ((uint32_t)(r1 & 0xFF) << 8) | ((uint32_t)(r2 & 0xFF) << 16) | ((uint32_t)r3 << 24);
+                        }
+                        *reinterpret_cast<uint4 *>(stg + c0)      = make_uint4(w[0], w[1], w[2], w[3]);
+                        *reinterpret_cast<uint4 *>(stg + c0 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+                    }
+                    fence_proxy_async(); // generic-proxy writes of this thread -> visible to the async (copy engine) proxy
+                    if (col_ok)
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + h0), "r"(stg_s), "r"(SCAT_ROWS) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else if constexpr (EPI == EPI_RAW_I32_SCATTER) {
+                // 32 rows x 4 B = 128 B per column and TMEM chunk: same staging row, one bulk copy per chunk
+                int32_t *dst = reinterpret_cast<int32_t *>(out_base) + (size_t)tc.unit * P.out_stride + (size_t)col_o * P.ldc + row0;
+                unsigned char *stg = smem + NUM_STAGES * KS::STAGE + 256 + (warp - 2) * SCAT_WARP_BYTES + lane * SCAT_PITCH;
+                const uint32_t stg_s = smem_u32(stg);
+#pragma unroll 1
+                for (int c0 = 0; c0 < TILE_COL; c0 += 32) {
+                    int32_t v[32];
+                    tmem_ld32(taddr0 + c0, v);
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<int4 *>(stg + 16 * j) = make_int4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    fence_proxy_async();
+                    if (col_ok)
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + c0), "r"(stg_s), "r"(128) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
             } else if constexpr (EPI == EPI_RAW_I32) {
-                int32_t *dst = reinterpret_cast<int32_t *>(P.out) + (size_t)tc.unit * P.out_stride + (size_t)col_c * P.ldc + row0;
+                int32_t *dst = reinterpret_cast<int32_t *>(out_base) + (size_t)tc.unit * P.out_stride + (size_t)col_o * P.ldc + row0;
 #pragma unroll 1
                 for (int c0 = 0; c0 < TILE_COL; c0 += 32) {
                     int32_t v[32];
@@ -607,6 +678,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
         }
     }
 
+    if constexpr (EPI == EPI_MOD_I8_SCATTER || EPI == EPI_RAW_I32_SCATTER) {
+        if (warp >= 2) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // all bulk stores of this thread have been written
+    }
     tc_fence_before();
     if constexpr (CG == 2) cluster_sync_all(); // neither CTA may exit (or free TMEM) while the pair's MMAs / remote arrives are in flight
     else __syncthreads();
@@ -692,6 +766,14 @@ template <int EPI, int CG> static int launch_tc_cg(const GemmArgs &g, cudaStream
     P.out = g.out, P.out_stride = g.out_stride, P.ldc = g.ldc;
     P.rowmax = g.rowmax, P.colmax = g.colmax;
     P.inflate = (float)(g.k_true + 1) * 0x1p-24f;
+    P.owner_cols = 0, P.tl_rot = 0;
+    if (g.owner_cols) {
+        // the scatter is tile-granular: every lane tile (TILE_LANE * CG columns) must fall inside one owner's slab
+        if (g.owner_cols % (TILE_LANE * CG) || (EPI != EPI_MOD_I8_SCATTER && EPI != EPI_RAW_I32_SCATTER)) return (int)cudaErrorInvalidValue;
+        P.owner_cols = (int)g.owner_cols;
+        for (int i = 0; i < G8_MAX_PEERS; ++i) P.peer_out[i] = g.peer_out[i];
+        P.tl_rot = (int)(((size_t)(g.rank + 1) % (size_t)g.world) * (g.owner_cols / (TILE_LANE * CG))) % P.tiles_l;
+    }
 
     static bool attr_set = false;
     if (!attr_set) {
@@ -717,8 +799,8 @@ template <int EPI> static int launch_tc(const GemmArgs &g, cudaStream_t st) {
 
 int launch_gemm_tc(const GemmArgs &g, cudaStream_t st) {
     switch (g.epi) {
-    case EPI_MOD_I8: return launch_tc<EPI_MOD_I8>(g, st);
-    case EPI_RAW_I32: return launch_tc<EPI_RAW_I32>(g, st);
+    case EPI_MOD_I8: return g.owner_cols ? launch_tc<EPI_MOD_I8_SCATTER>(g, st) : launch_tc<EPI_MOD_I8>(g, st);
+    case EPI_RAW_I32: return g.owner_cols ? launch_tc<EPI_RAW_I32_SCATTER>(g, st) : launch_tc<EPI_RAW_I32>(g, st);
     case EPI_BOUND_MAX: return launch_tc<EPI_BOUND_MAX>(g, st);
     case EPI_MOD_I8_CPLX: return launch_tc<EPI_MOD_I8_CPLX>(g, st);
     case EPI_BOUND_MAX_CPLX: return launch_tc<EPI_BOUND_MAX_CPLX>(g, st);

@@ -39,6 +39,10 @@ enum GemmEpilogue : int {
     EPI_F8_MOD   = 5, // three products per modulus (square moduli: AhBl, AlBh, AlBl; else Karatsuba) -> int16 residue
     EPI_F8_BOUND = 6, // bound product (one plane each), inflated by (k+1)*2^-24, row/col float maxima
     EPI_F8_RAW   = 7, // TEST ONLY: raw f32 accumulator of one product per unit
+    // K-sharded multi-GPU: EPI_MOD_I8 whose residue tiles leave through shared memory + cp.async.bulk (128-byte column segments)
+    // into the owning rank's peer-mapped buffer.  Selected internally when GemmArgs::owner_cols != 0.
+    EPI_MOD_I8_SCATTER = 8,
+    EPI_RAW_I32_SCATTER = 9, // same for the raw INT32 partial (the bound product of accurate mode)
 };
 
 struct GemmArgs {
@@ -58,6 +62,10 @@ struct GemmArgs {
     size_t out_stride;   // elements between output planes
     size_t ldc;          // leading dimension of the output (m_pad)
     int32_t *rowmax, *colmax;
+    // K-sharded multi-GPU, fused GEMM -> scatter (EPI_MOD_I8 / EPI_RAW_I32 only): see KParams in g8_gemm_i8.cu
+    void *peer_out[G8_MAX_PEERS];
+    size_t owner_cols; // 0 = plain single-buffer output
+    int rank, world;
 };
 // tcgen05 path (product).  Returns cudaError_t-compatible int.
 int launch_gemm_tc(const GemmArgs &g, cudaStream_t st);
@@ -76,6 +84,10 @@ struct CrtArgs {
     const int16_t *sftA, *sftB;
     const void *alpha, *beta; // host or device pointers (resolved by the launcher)
     int backend;              // INT8: int8 residues, FP8: int16 residues and the FP8 moduli tables
+    // K-sharded multi-GPU (INT8 backend): C_mid is `nparts` per-shard residue arrays `part_stride` bytes apart; the residue fed to
+    // the CRT is sym((sum over parts) mod p_i).  nparts <= 1: plain C_mid.
+    int nparts;
+    size_t part_stride;
 };
 int launch_crt(const CrtArgs &c, int dtype, cudaStream_t st);
 

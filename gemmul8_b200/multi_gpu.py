@@ -13,6 +13,10 @@ and the exact integer structure of Ozaki-II makes the sharding exact:
   contraction  local tcgen05 INT8 GEMMs over all moduli; then ONE collective:
             variant "int32"  : raw INT32 partials [col][modulus][row]  -> reduce_scatter(SUM, int32)   (the north-star wording)
             variant "residue": partials reduced mod p in the GEMM epilogue (int8) -> all_to_all (4x fewer bytes) -> sum + mod
+            variant "fused"  : ONE kernel does the GEMM and the exchange -- the tcgen05 epilogue stores each residue tile straight into
+                               the owning rank's buffer over NVLink (peer memory mapped with CUDA IPC), so the transfer overlaps the
+                               math tile by tile; a 1-element all_reduce orders the ranks, then sum + mod.  Accurate mode scatters its
+                               INT32 bound partial the same way.  What bench.py --gpus N uses.
   CRT       every rank reconstructs its column slab C[:, n_r] (`g8_stage_crt`)
 
 Exactness: |sum| <= K_total * 2^14 < 2^31 for K_total <= 2^17, so the INT32 reduction cannot overflow; the residue variant
@@ -24,6 +28,7 @@ implementation built on the oracle to exercise THIS file's orchestration with th
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -38,6 +43,8 @@ def pad256(x: int) -> int:
 
 class CudaStages:
     """Stage kernels through include/gemmul8_c.h on CUDA tensors.  No fallback: fails if the library or an sm_100a device is missing."""
+
+    scatter_granularity = 256  # columns: the fused GEMM -> scatter hands whole 256-column tiles to one owner
 
     def __init__(self, dtype, num_moduli, device):
         from . import _lib
@@ -72,6 +79,21 @@ class CudaStages:
         api._check(self.lib.g8_stage_gemm(epi, 0, A_lo.data_ptr(), strideA, B_lo.data_ptr(), strideB, m, n, k_pad, units, first, None, None,
                                           out.data_ptr(), out_stride, ldc, None, None, self._s()), "gemm")
 
+    # ---- peer-mapped buffers (CUDA IPC) and the fused GEMM -> scatter ----
+    def peer_buffer(self, nbytes, group=None):
+        """Allocate `nbytes` on this rank, map the same buffer of every other rank; returns PeerBuffer (local tensor view + pointer table)."""
+        return PeerBuffer(self.lib, nbytes, self.dev, group)
+
+    def gemm_scatter(self, epi, A_lo, strideA, B_lo, strideB, m, n, k_pad, units, peers, elem_offset_bytes, out_stride, ldc, first=0):
+        W = len(peers.ptrs)
+        tbl = (ctypes.c_void_p * W)(*[p + elem_offset_bytes for p in peers.ptrs])
+        api._check(self.lib.g8_stage_gemm_scatter(epi, A_lo.data_ptr(), strideA, B_lo.data_ptr(), strideB, m, n, k_pad, units, first, tbl, W,
+                                                  peers.rank, out_stride, ldc, self._s()), "gemm_scatter")
+
+    def maxabs_parts(self, parts, nparts, part_stride, rows, cols, ld, rowmax, colmax):
+        api._check(self.lib.g8_stage_maxabs_i32_parts(parts.data_ptr(), nparts, part_stride, rows, cols, ld, rowmax.data_ptr(), colmax.data_ptr(),
+                                                      self._s()), "maxabs_parts")
+
     def maxabs(self, C, rows, cols, ld, rowmax, colmax):
         api._check(self.lib.g8_stage_maxabs_i32(C.data_ptr(), rows, cols, ld, rowmax.data_ptr(), colmax.data_ptr(), self._s()), "maxabs")
 
@@ -85,11 +107,58 @@ class CudaStages:
         api._check(self.lib.g8_stage_residue_sum(parts.data_ptr(), nparts, part_stride, rows, cols, in_ld, in_us, units, first, C_mid.data_ptr(),
                                                  out_ld, out_us, self._s()), "residue_sum")
 
+    def crt_parts(self, parts, nparts, part_stride, ldmid, plane_stride, m, n, C, ldc, sftA, sftB, alpha, beta):
+        keep = []
+        pa, pb = api._scalar_ptr(alpha, self.dtype, keep), api._scalar_ptr(beta, self.dtype, keep)
+        api._check(self.lib.g8_stage_crt_parts(self.dt, parts.data_ptr(), nparts, part_stride, ldmid, plane_stride, m, n, self.N, C.data_ptr(), ldc,
+                                               sftA.data_ptr(), sftB.data_ptr(), pa, pb, self._s()), "crt_parts")
+
     def crt(self, C_mid, ldmid, plane_stride, m, n, C, ldc, sftA, sftB, alpha, beta):
         keep = []
         pa, pb = api._scalar_ptr(alpha, self.dtype, keep), api._scalar_ptr(beta, self.dtype, keep)
         api._check(self.lib.g8_stage_crt(self.dt, C_mid.data_ptr(), ldmid, plane_stride, m, n, self.N, C.data_ptr(), ldc, sftA.data_ptr(),
                                          sftB.data_ptr(), pa, pb, self._s()), "crt")
+
+
+class _RawCuda:
+    """__cuda_array_interface__ view of a raw device allocation (so torch can wrap memory we cudaMalloc'ed for IPC)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+class PeerBuffer:
+    """One device buffer per rank, each mapped into every rank of the node with CUDA IPC (g8_peer_alloc / g8_peer_open).
+    ptrs[o] is rank o's buffer as seen from THIS process; `local` is this rank's buffer as a uint8 torch tensor."""
+
+    def __init__(self, lib, nbytes, device, group=None):
+        self.lib, self.group = lib, group
+        self.rank, W = dist.get_rank(group), dist.get_world_size(group)
+        handle = ctypes.create_string_buffer(64)
+        p = ctypes.c_void_p()
+        api._check(lib.g8_peer_alloc(nbytes, ctypes.byref(p), handle), "peer_alloc")
+        self.own = p.value
+        handles = [None] * W
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.ptrs, self.opened = [], []
+        for o in range(W):
+            if o == self.rank:
+                self.ptrs.append(self.own)
+                continue
+            q = ctypes.c_void_p()
+            api._check(lib.g8_peer_open(ctypes.create_string_buffer(handles[o], 64), ctypes.byref(q)), "peer_open")
+            self.ptrs.append(q.value)
+            self.opened.append(q.value)
+        self.local = torch.as_tensor(_RawCuda(self.own, nbytes), device=device)
+
+    def close(self):
+        for q in self.opened:
+            self.lib.g8_peer_close(q)
+        self.opened = []
+        if self.own:
+            dist.barrier(group=self.group)  # nobody may still have our buffer mapped when it is freed
+            self.lib.g8_peer_free(self.own)
+            self.own = None
 
 
 # ---- collectives (NCCL on GPUs; the gloo branches exist for the CPU tests of this orchestration) ----
@@ -155,13 +224,29 @@ class KShardGemm:
         G = max(1, min(pipeline_groups, N))
         self.batches = [(i * N // G, (i + 1) * N // G - i * N // G) for i in range(G)]  # (first modulus, count)
         per = n * N * self.m_pad
-        self.part = st.empty(per, torch.int32 if variant == "int32" else torch.int8)      # per batch: [col][modulus in batch][row]
-        self.recv = st.empty(per // self.W if variant == "int32" else per, self.part.dtype)  # my column slab (x world for residue)
-        self.C_mid = st.empty(N * self.nc * self.m_pad, torch.int8)                         # [modulus][col][row]
-        if not self.fast:
+        self.C_mid = None if variant == "fused" else st.empty(N * self.nc * self.m_pad, torch.int8)  # [modulus][col][row]
+        self.peers = None
+        if variant == "fused":
+            if self.nc % st.scatter_granularity:
+                raise ValueError(f"fused variant: n / world must be a multiple of {st.scatter_granularity} (the scatter is tile-granular)")
+            # this rank's receive area, written by every rank's GEMM epilogue: [src rank][modulus][col in slab][row] int8, followed
+            # (accurate mode) by [src rank][col in slab][row] int32 for the bound partial
+            self.recv_bytes = per
+            self.cbar_off = per
+            total = per + (0 if self.fast else 4 * self.W * self.nc * self.m_pad)
+            self.peers = st.peer_buffer(total, group)
+            self.recv = self.peers.local[:per].view(torch.int8)
+            if not self.fast:
+                self.cbar_parts = self.peers.local[per:].view(torch.int32)
+            self.token = st.zeros(1, torch.int32)
+        else:
+            self.part = st.empty(per, torch.int32 if variant == "int32" else torch.int8)      # per batch: [col][modulus in batch][row]
+            self.recv = st.empty(per // self.W if variant == "int32" else per, self.part.dtype)  # my column slab (x world for residue)
+        if not self.fast and variant != "fused":
             self.cbar = st.empty(n * self.m_pad, torch.int32)
             self.cbar_slab = st.empty(self.nc * self.m_pad, torch.int32)
         self.local_out_elems = m * self.nc
+        self._trace = None
 
     def local_out(self, C):
         return C[:self.local_out_elems]
@@ -170,6 +255,7 @@ class KShardGemm:
         st, m, n, k, N = self.st, self.m, self.n, self.k, self.N
         amaxA, ssA = st.stats(True, 0, m, k, A, m)
         amaxB, ssB = st.stats(False, 0, n, k, B, k)
+        self._mark("stats")
         both_max = torch.cat([amaxA, amaxB])
         dist.all_reduce(both_max, op=dist.ReduceOp.MAX, group=self.group)
         amaxA, amaxB = both_max[:m], both_max[m:]
@@ -184,11 +270,22 @@ class KShardGemm:
         st.shift_from_stats(amaxB.contiguous(), None, 1, self.sftB)
         st.split(True, 0, m, k, A, m, 3, self.sftA, self.A_lo, self.sizeA)
         st.split(False, 0, n, k, B, k, 3, self.sftB, self.B_lo, self.sizeB)
-        st.gemm(1, self.A_lo, self.sizeA, self.B_lo, self.sizeB, m, n, self.k_pad, 1, self.cbar, 0, self.m_pad)
-        reduce_scatter_sum(self.cbar_slab, self.cbar, self.group)
+        self._mark("bound planes")
         rowmax = st.zeros(self.m_pad, torch.int32)
         colmax_slab = st.zeros(self.nc, torch.int32)
-        st.maxabs(self.cbar_slab, m, self.nc, self.m_pad, rowmax, colmax_slab)
+        if self.variant == "fused":
+            # INT32 bound partial scattered by the GEMM epilogue into the owners' [src rank][col][row] areas, then summed + maxed there
+            slab = self.nc * self.m_pad
+            st.gemm_scatter(1, self.A_lo, self.sizeA, self.B_lo, self.sizeB, m, n, self.k_pad, 1, self.peers,
+                            self.cbar_off + 4 * self.rank * slab, 0, self.m_pad)
+            self._mark("bound gemm+scatter")
+            self._rank_barrier()
+            st.maxabs_parts(self.cbar_parts, self.W, slab, m, self.nc, self.m_pad, rowmax, colmax_slab)
+        else:
+            st.gemm(1, self.A_lo, self.sizeA, self.B_lo, self.sizeB, m, n, self.k_pad, 1, self.cbar, 0, self.m_pad)
+            reduce_scatter_sum(self.cbar_slab, self.cbar, self.group)
+            st.maxabs(self.cbar_slab, m, self.nc, self.m_pad, rowmax, colmax_slab)
+        self._mark("bound max")
         dist.all_reduce(rowmax, op=dist.ReduceOp.MAX, group=self.group)
         colmax = st.zeros(self.n, torch.int32)
         dist.all_gather_into_tensor(colmax, colmax_slab, group=self.group) if not _is_gloo(self.group) else \
@@ -196,13 +293,54 @@ class KShardGemm:
         st.finalize_shift(self.sftA, rowmax, m)
         st.finalize_shift(self.sftB, colmax, n)
 
+    def _rank_barrier(self):
+        """Stream-ordered barrier across the ranks: a 1-element all_reduce.  It cannot complete on any rank before every rank has
+        enqueued it, i.e. before every rank's preceding kernel (the scatter GEMM) has finished -- kernel completion makes its peer
+        stores visible system-wide."""
+        dist.all_reduce(self.token, op=dist.ReduceOp.MAX, group=self.group)
+
+    def close(self):
+        if self.peers is not None:
+            self.peers.close()
+            self.peers = None
+
+    # ---- optional phase trace (G8_MG_TRACE=1): CUDA events on the compute stream, reported by trace_report() ----
+    def _mark(self, name):
+        if self._trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._trace.append((name, e))
+
+    def trace_report(self):
+        """[(phase, ms)] of the last run() when tracing is on (synchronises)."""
+        if not self._trace:
+            return []
+        torch.cuda.synchronize()
+        return [(self._trace[i + 1][0], self._trace[i][1].elapsed_time(self._trace[i + 1][1])) for i in range(len(self._trace) - 1)]
+
     def run(self, A, B, C, alpha=1.0, beta=0.0):
         """A: flat m*k_local, B: flat k_local*n (this rank's K-slab), C: flat buffer receiving the m x (n/world) slab (ld = m)."""
         st, m, n, k, N = self.st, self.m, self.n, self.k, self.N
+        self._trace = [] if (os.environ.get("G8_MG_TRACE") == "1" and torch.cuda.is_available()) else None
+        self._mark("start")
         self._shifts(A, B)
+        self._mark("shifts")
         st.split(True, 0, m, k, A, m, 0, self.sftA, self.A_lo, self.sizeA)
         st.split(False, 0, n, k, B, k, 0, self.sftB, self.B_lo, self.sizeB)
+        self._mark("split")
         mp, nc, W = self.m_pad, self.nc, self.W
+        if self.variant == "fused":
+            # (the collectives of _shifts above ordered this step after every rank's reads of the previous step's receive area)
+            st.gemm_scatter(0, self.A_lo, self.sizeA, self.B_lo, self.sizeB, m, n, self.k_pad, N, self.peers,
+                            self.rank * N * nc * mp, nc * mp, mp)
+            self._mark("gemm+scatter")
+            self._rank_barrier()
+            self._mark("barrier")
+            r0 = self.rank * nc
+            # the CRT sums the per-shard residues itself (no separate sum pass, no C_mid round trip)
+            st.crt_parts(self.recv, W, N * nc * mp, mp, nc * mp, m, nc, C, m, self.sftA, self.sftB[r0:r0 + nc], alpha, beta)
+            self._mark("sum+crt")
+            return C
         pending = []  # (handle, batch) whose exchange is in flight
 
         def finish(h, u0, nu, recv):
@@ -230,6 +368,8 @@ class KShardGemm:
             pending.append((h, u0, nu, recv))
         while pending:
             finish(*pending.pop(0))
+        self._mark("gemm+exchange+requant")
         r0 = self.rank * nc
         st.crt(self.C_mid, mp, nc * mp, m, nc, C, m, self.sftA, self.sftB[r0:r0 + nc], alpha, beta)
+        self._mark("crt")
         return C

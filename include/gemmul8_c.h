@@ -94,6 +94,12 @@ int g8_stage_gemm(int epilogue, int use_simt, const int8_t *A_lo, size_t strideA
 int g8_stage_crt(int dtype, const void *C_mid, size_t ldmid, size_t plane_stride, size_t m, size_t n, unsigned num_moduli, void *C,
                  size_t ldc, const int16_t *sftA, const int16_t *sftB, const void *alpha, const void *beta, void *stream);
 
+/* Stage 3 on per-shard residues (K-sharded multi-GPU, real types, INT8 backend): the residue of modulus i is
+ * sym((sum_q parts[q]) mod p_i), parts `part_stride` bytes apart, each laid out like C_mid; then exactly g8_stage_crt. */
+int g8_stage_crt_parts(int dtype, const void *parts, int nparts, size_t part_stride, size_t ldmid, size_t plane_stride, size_t m, size_t n,
+                       unsigned num_moduli, void *C, size_t ldc, const int16_t *sftA, const int16_t *sftB, const void *alpha, const void *beta,
+                       void *stream);
+
 /* ---- K-sharded multi-GPU support (new work; the reference is single-GPU) ---- */
 
 /* C_mid[u][col][row] = sym(C_hi[u][col][row] mod p_u) for int32 partial products that were summed across K-shards
@@ -102,12 +108,34 @@ int g8_stage_crt(int dtype, const void *C_mid, size_t ldmid, size_t plane_stride
 int g8_stage_requant_i32(const int32_t *C_hi, size_t rows, size_t cols, size_t in_ld, size_t in_unit_stride, int num_units,
                          int first_modulus, int8_t *C_mid, size_t out_ld, size_t out_unit_stride, void *stream);
 
-/* Residue variant: every shard reduced its partial mod p locally (int8); sum `nparts` such arrays and reduce again. */
+/* Residue variant: every shard reduced its partial mod p locally (int8); sum `nparts` such arrays and reduce again.
+ * rows, all strides and both base pointers must be multiples of 16 (128-bit accesses). */
 int g8_stage_residue_sum(const int8_t *parts, int nparts, size_t part_stride, size_t rows, size_t cols, size_t in_ld, size_t in_unit_stride,
                          int num_units, int first_modulus, int8_t *C_mid, size_t out_ld, size_t out_unit_stride, void *stream);
 
 /* rowmax[r] = max(rowmax[r], C[r, c]), colmax[c] likewise, over an int32 slab (reduced bound product of accurate mode) */
 int g8_stage_maxabs_i32(const int32_t *C, size_t rows, size_t cols, size_t ld, int32_t *rowmax, int32_t *colmax, void *stream);
+
+/* Same, on the SUM of `nparts` int32 slabs (one per K-shard, `part_stride` elements apart): the bound product of accurate mode
+ * after the fused GEMM -> scatter below. */
+int g8_stage_maxabs_i32_parts(const int32_t *parts, int nparts, size_t part_stride, size_t rows, size_t cols, size_t ld, int32_t *rowmax,
+                              int32_t *colmax, void *stream);
+
+/* Fused GEMM -> scatter over NVLink peer memory (no reference counterpart; replaces "GEMM, then NCCL all-to-all / reduce-scatter"):
+ * the tcgen05 epilogue stores columns [o*n/world, (o+1)*n/world) of every unit's product directly into peer_out[o], a buffer of
+ * rank o mapped with g8_peer_open (peer_out[rank] is this rank's own buffer), at column (c - o*n/world), leading dimension ldc,
+ * unit stride out_stride.  epilogue 0: int8 residues mod p; 1: raw int32 partials.  n/world must be a multiple of 256.
+ * peer_out is a HOST array of `world` device pointers.  The caller orders the ranks (a collective before and after). */
+int g8_stage_gemm_scatter(int epilogue, const int8_t *A_lo, size_t strideA, const int8_t *B_lo, size_t strideB, size_t m, size_t n, size_t k_pad,
+                          int num_units, int first_modulus, void *const *peer_out, int world, int rank, size_t out_stride, size_t ldc,
+                          void *stream);
+
+/* Device buffers mappable by the other ranks of the node: cudaMalloc + cudaIpcGetMemHandle (64-byte handle, exchanged by the host
+ * side with any transport), cudaIpcOpenMemHandle / CloseMemHandle on the importing side. */
+int g8_peer_alloc(size_t bytes, void **dptr, void *handle64);
+int g8_peer_open(const void *handle64, void **dptr);
+int g8_peer_close(void *dptr);
+int g8_peer_free(void *dptr);
 
 /* Local row statistics of op(X) (rows x k view, is_A as in g8_stage_split): amax[r] = max |x|, sumsq[r] = round-up sum of x^2 */
 int g8_stage_stats(int dtype, int is_A, int op, size_t rows, size_t k, const void *X, size_t ld, double *amax, double *sumsq, void *stream);

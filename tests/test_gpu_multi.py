@@ -31,7 +31,7 @@ def _worker(rank, world, port, q):
 
         ok_all = True
         for dtype, N in ((torch.float64, 14), (torch.float32, 6)):
-            m, n, kl = 300, 256, 384
+            m, n, kl = 300, 256 * world, 384   # n / world = 256: one scatter tile per owner
             K = kl * world
             # full operands (same on every rank), column-major
             A = g8.randmat(m, K, dtype, phi=0.5, seed=11, device=f"cuda:{rank}")
@@ -43,11 +43,13 @@ def _worker(rank, world, port, q):
                 tot, _, _ = g8.work_size(m, n, K, N)
                 work = torch.empty(tot, dtype=torch.uint8, device=f"cuda:{rank}")
                 g8.gemm("N", "N", m, n, K, 1.0, A, m, B, K, 0.0, Cfull, m, N, fast, work)
-                for variant in ("int32", "residue"):
+                for variant in ("int32", "residue", "fused"):
                     plan = multi_gpu.KShardGemm(m, n, kl, N, fastmode=fast, dtype=dtype, device=f"cuda:{rank}", variant=variant)
                     C = torch.zeros(plan.local_out_elems, dtype=dtype, device=f"cuda:{rank}")
-                    plan.run(Ar, Br, C)
+                    for _ in range(2 if variant == "fused" else 1):   # the fused variant re-uses peer-mapped receive areas across steps
+                        plan.run(Ar, Br, C)
                     torch.cuda.synchronize()
+                    plan.close()
                     nc = n // world
                     want = Cfull.view(n, m)[rank * nc:(rank + 1) * nc].reshape(-1)
                     if not fast:

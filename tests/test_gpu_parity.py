@@ -200,3 +200,78 @@ def test_host_pipeline_bitwise(env, dtype, N, fast):
         assert H.bits_equal(got, want), H.first_diff(got, want, f"C {opA}{opB}")
         if ldc > m:  # padding rows of the caller's buffer must be untouched
             assert np.array_equal(hC.numpy().reshape(n, ldc)[:, m:], sentinel.numpy().reshape(n, ldc)[:, m:])
+
+
+@pytest.mark.parametrize("nparts", [2, 8])
+@pytest.mark.parametrize("dtype,N", [(np.float64, 14), (np.float32, 6)])
+def test_kshard_stage_kernels_on_one_gpu(env, nparts, dtype, N):
+    """K-sharded helpers: g8_stage_crt_parts (CRT that sums per-shard residues) == g8_stage_residue_sum + g8_stage_crt, bit for
+    bit, and both == the oracle's CRT on the numpy sum; the fused GEMM -> scatter with every 'peer' mapped to buffers of THIS GPU
+    == the plain GEMM epilogue."""
+    torch, H, lib, api, T, O = env.torch, env.H, env.lib, env.api, env.T, env.O
+    rng = np.random.default_rng(nparts * 100 + N)
+    m, n = 300, 40
+    mp = api.pad256(m)
+    mods = T.moduli("INT8")[:N]
+    parts = rng.integers(-127, 128, size=(nparts, N, n, mp)).astype(np.int8)
+    for i, p in enumerate(mods):
+        parts[:, i] = np.clip(parts[:, i], -(p // 2), p // 2)
+    sA = rng.integers(-60, -20, size=m).astype(np.int16)
+    sB = rng.integers(-60, -20, size=n).astype(np.int16)
+    tot = parts.astype(np.int64).sum(axis=0)
+    cm = np.empty((N, n, mp), dtype=np.int8)
+    for i, p in enumerate(mods):
+        r = np.mod(tot[i], p)
+        cm[i] = np.where(r > p // 2, r - p, r).astype(np.int8)
+    want = O.crt(cm, m, n, N, sA, sB, dtype, 1.0, 0.0)
+    tdt = H.NP2T[np.dtype(dtype)]
+    dparts = torch.from_numpy(parts).cuda()
+    dsA = torch.zeros(mp, dtype=torch.int16, device="cuda"); dsA[:m] = torch.from_numpy(sA).cuda()
+    dsB = torch.zeros(api.pad256(n), dtype=torch.int16, device="cuda"); dsB[:n] = torch.from_numpy(sB).cuda()
+    keep = []
+    pa, pb = api._scalar_ptr(1.0, tdt, keep), api._scalar_ptr(0.0, tdt, keep)
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for fusedsum in (True, False):
+        dC = torch.zeros(n * m, dtype=tdt, device="cuda")
+        if fusedsum:
+            code = lib.g8_stage_crt_parts(api._DTYPES[tdt], dparts.data_ptr(), nparts, N * n * mp, mp, n * mp, m, n, N, dC.data_ptr(), m,
+                                          dsA.data_ptr(), dsB.data_ptr(), pa, pb, st)
+        else:
+            dmid = torch.zeros(N * n * mp, dtype=torch.int8, device="cuda")
+            code = lib.g8_stage_residue_sum(dparts.data_ptr(), nparts, N * n * mp, mp, n, mp, n * mp, N, 0, dmid.data_ptr(), mp, n * mp, st)
+            assert code == 0
+            assert np.array_equal(dmid.cpu().numpy().reshape(N, n, mp), cm)
+            code = lib.g8_stage_crt(api._DTYPES[tdt], dmid.data_ptr(), mp, n * mp, m, n, N, dC.data_ptr(), m, dsA.data_ptr(), dsB.data_ptr(), pa, pb, st)
+        assert code == 0
+        torch.cuda.synchronize()
+        outs.append(dC.cpu().numpy().reshape(n, m).T.copy())
+    assert H.bits_equal(outs[0], outs[1])
+    assert H.bits_equal(outs[0], want), H.first_diff(outs[0], want, "C")
+
+
+def test_gemm_scatter_local_peers(env):
+    """the scatter epilogues (shared-memory staging + cp.async.bulk) with world = 2 'ranks' whose buffers both live on this GPU:
+    rank r's columns land in peer_out[r] exactly as the plain epilogues would have written them."""
+    import ctypes
+    torch, lib, api = env.torch, env.lib, env.api
+    m, n, k_pad, N = 300, 512, 512, 3
+    mp = api.pad256(m)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A_lo = torch.randint(-127, 128, (N, mp, k_pad), dtype=torch.int8, device="cuda", generator=g)
+    B_lo = torch.randint(-127, 128, (N, n, k_pad), dtype=torch.int8, device="cuda", generator=g)
+    st = torch.cuda.current_stream().cuda_stream
+    nc = n // 2
+    for epi, tdt in ((0, torch.int8), (1, torch.int32)):
+        ref = torch.zeros(N, n, mp, dtype=tdt, device="cuda")
+        assert lib.g8_stage_gemm(epi, 0, A_lo.data_ptr(), mp * k_pad, B_lo.data_ptr(), n * k_pad, m, n, k_pad, N, 0, None, None, ref.data_ptr(),
+                                 n * mp, mp, None, None, st) == 0
+        bufs = [torch.full((N, nc, mp), 77, dtype=tdt, device="cuda") for _ in range(2)]
+        tbl = (ctypes.c_void_p * 2)(bufs[0].data_ptr(), bufs[1].data_ptr())
+        for rank in (0, 1):  # the rank only changes the tile rotation
+            for b in bufs:
+                b.fill_(77)
+            assert lib.g8_stage_gemm_scatter(epi, A_lo.data_ptr(), mp * k_pad, B_lo.data_ptr(), n * k_pad, m, n, k_pad, N, 0, tbl, 2, rank, nc * mp, mp, st) == 0
+            torch.cuda.synchronize()
+            for o in (0, 1):
+                assert torch.equal(bufs[o][:, :, :m], ref[:, o * nc:(o + 1) * nc, :m]), (epi, rank, o)

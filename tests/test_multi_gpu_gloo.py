@@ -24,8 +24,61 @@ def pad256(x):
     return 256 * ((x + 255) // 256)
 
 
+class ShmPeerBuffer:
+    """CPU stand-in for multi_gpu.PeerBuffer: one /dev/shm file per rank, mapped by every rank (what CUDA IPC does for HBM)."""
+
+    def __init__(self, nbytes, group=None):
+        self.rank, W = dist.get_rank(group), dist.get_world_size(group)
+        tag = os.environ.get("MASTER_PORT", "0")
+        self.paths = [f"/dev/shm/g8_gloo_test_{tag}_{id(self) % 1000}_{o}" for o in range(W)]
+        name = [self.paths[self.rank]]
+        np.memmap(name[0], dtype=np.uint8, mode="w+", shape=(nbytes,)).flush()
+        names = [None] * W
+        dist.all_gather_object(names, name[0], group=group)
+        self.paths = names
+        self.ptrs = [np.memmap(pth, dtype=np.uint8, mode="r+", shape=(nbytes,)) for pth in names]
+        self.local = torch.from_numpy(self.ptrs[self.rank])
+        self.group = group
+
+    def close(self):
+        dist.barrier(group=self.group)
+        self.ptrs = []
+        try:
+            os.unlink(self.paths[self.rank])
+        except OSError:
+            pass
+
+
 class OracleStages:
     """CPU stand-in for multi_gpu.CudaStages, built on oracle/ (numpy + g8_oracle.c)."""
+
+    scatter_granularity = 1
+
+    def peer_buffer(self, nbytes, group=None):
+        return ShmPeerBuffer(nbytes, group)
+
+    def gemm_scatter(self, epi, A_lo, strideA, B_lo, strideB, m, n, k_pad, units, peers, offset_bytes, out_stride, ldc, first=0):
+        a, b = A_lo.numpy(), B_lo.numpy()
+        W = len(peers.ptrs)
+        oc = n // W
+        dt = np.int8 if epi == 0 else np.int32
+        isz = np.dtype(dt).itemsize
+        for u in range(units):
+            Au = a[u * strideA:u * strideA + m * k_pad].reshape(m, k_pad).astype(np.int64)
+            Bu = b[u * strideB:u * strideB + n * k_pad].reshape(n, k_pad).astype(np.int64)
+            H = Au @ Bu.T
+            if epi == 0:
+                H = self._sym(H, self.mods[first + u])
+            for c in range(n):
+                o, cl = divmod(c, oc)
+                raw = peers.ptrs[o]
+                start = offset_bytes + (u * out_stride + cl * ldc) * isz
+                raw[start:start + m * isz] = np.ascontiguousarray(H[:, c].astype(dt)).view(np.uint8)
+
+    def maxabs_parts(self, parts, nparts, part_stride, rows, cols, ld, rowmax, colmax):
+        p = parts.numpy().astype(np.int64)
+        tot = sum(p[q * part_stride:q * part_stride + cols * ld] for q in range(nparts)).astype(np.int32)
+        self.maxabs(torch.from_numpy(tot), rows, cols, ld, rowmax, colmax)
 
     def __init__(self, dtype, N):
         from oracle import oracle as O
@@ -118,6 +171,11 @@ class OracleStages:
                 acc = sum(src[q * part_stride + u * in_us + c * in_ld:q * part_stride + u * in_us + c * in_ld + rows] for q in range(nparts))
                 dst[u * out_us + c * out_ld:u * out_us + c * out_ld + rows] = self._sym(acc, self.mods[first + u])
 
+    def crt_parts(self, parts, nparts, part_stride, ldmid, plane_stride, m, n, C, ldc, sftA, sftB, alpha, beta):
+        tmp = torch.zeros(self.N * n * ldmid, dtype=torch.int8)
+        self.residue_sum(parts, nparts, part_stride, ldmid, n, ldmid, plane_stride, self.N, tmp, ldmid, n * ldmid)
+        self.crt(tmp, ldmid, n * ldmid, m, n, C, ldc, sftA, sftB, alpha, beta)
+
     def crt(self, C_mid, ldmid, plane_stride, m, n, C, ldc, sftA, sftB, alpha, beta):
         cm = C_mid.numpy().reshape(self.N, n, ldmid)
         out = self.O.crt(np.ascontiguousarray(cm), m, n, self.N, sftA.numpy()[:m], sftB.numpy()[:n], self.dtype, alpha, beta)
@@ -150,6 +208,9 @@ def _worker(rank, world, port, variant, fast, dtype_name, q):
         plan = multi_gpu.KShardGemm(m, n, kl, N, fastmode=fast, dtype=t_dt, variant=variant, stages=OracleStages(np_dt, N))
         C = torch.zeros(plan.local_out_elems, dtype=t_dt)
         plan.run(tA, tB, C)
+        if variant == "fused":  # a second step re-uses the peer-mapped receive areas: the inter-step ordering must hold
+            C.zero_()
+            plan.run(tA, tB, C)
         nc = n // world
         got = C.numpy().reshape(nc, m).T
         sA, sB = plan.sftA.numpy()[:m].copy(), plan.sftB.numpy()[:n].copy()
@@ -157,6 +218,7 @@ def _worker(rank, world, port, variant, fast, dtype_name, q):
         ref = O.emulate(A, B, "N", "N", N, fast, sftA=None if not fast else sA, sftB=None if not fast else sB)
         ok_shift = np.array_equal(ref["sftA"], sA) and np.array_equal(ref["sftB"], sB)
         ok = np.array_equal(np.ascontiguousarray(got).view(np.uint8), np.ascontiguousarray(ref["C"][:, rank * nc:(rank + 1) * nc]).view(np.uint8))
+        plan.close()
         q.put((rank, bool(ok), bool(ok_shift)))
     except Exception as e:  # report instead of letting the parent wait for the queue timeout
         q.put((rank, False, False))
@@ -165,7 +227,7 @@ def _worker(rank, world, port, variant, fast, dtype_name, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("variant", ["int32", "residue"])
+@pytest.mark.parametrize("variant", ["int32", "residue", "fused"])
 @pytest.mark.parametrize("fast", [False, True])
 @pytest.mark.parametrize("dtype_name", ["float64", "float32"])
 def test_kshard_two_ranks_matches_single_process(variant, fast, dtype_name):
