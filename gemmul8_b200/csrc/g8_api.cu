@@ -346,11 +346,11 @@ __attribute__((visibility("default"))) int g8_stage_crt_parts(int dtype, const v
                                                                const void *beta, void *stream) {
     if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
     if (!parts || !C || !sftA || !sftB || !alpha || !beta || num_moduli < 2 || num_moduli > G8_MAX_MODULI) return G8_STATUS_INVALID_VALUE;
-    if (nparts < 1 || nparts > 64 || part_stride % 4 || (dtype != F32 && dtype != F64)) return G8_STATUS_INVALID_VALUE;
+    if (nparts < 1 || nparts > G8_MAX_PEERS || part_stride % 4 || (dtype != F32 && dtype != F64)) return G8_STATUS_INVALID_VALUE;
     CrtArgs c{};
     c.C_mid = parts, c.ldmid = ldmid, c.plane_stride = plane_stride, c.m = m, c.n = n, c.num_moduli = (int)num_moduli;
     c.C = C, c.ldc = ldc, c.sftA = sftA, c.sftB = sftB, c.alpha = alpha, c.beta = beta;
-    c.nparts = nparts, c.part_stride = part_stride;
+    c.nparts = nparts, c.part_stride = part_stride, c.backend = INT8;
     return launch_crt(c, dtype, static_cast<cudaStream_t>(stream));
 }
 

@@ -38,7 +38,8 @@ constexpr int CRT_NV = 4; // residue bytes (= scalar outputs) per thread: one 32
                           // small per-thread state -> full occupancy hides the serial FMA chains
 
 // MODE: 0 C=AB, 1 C+=AB, 2 C=-AB, 3 C-=AB, 4 general (host scalars), 5 general (device scalars)
-template <typename T, bool DD, int MODE, bool VECIO, int BE>
+// PARTS: 0 = plain C_mid; 2 / 4 / 8 = K-sharded, up to that many per-shard residue arrays (c.nparts of them are real)
+template <typename T, bool DD, int MODE, bool VECIO, int BE, int PARTS = 0>
 __global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t groups, size_t total) {
     using TR           = CrtTraits<T>;
     using U            = typename TR::U;
@@ -65,16 +66,22 @@ __global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t 
         double cd[NV];
         if constexpr (BE == INT8) {
             uint32_t w;
-            if (c.nparts <= 1) {
+            if constexpr (PARTS == 0) {
                 w = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)i * pstride));
             } else {
                 // K-sharded: add the per-shard residues byte-wise (dp4a against one-hot selectors sign-extends and adds in one
                 // instruction), reduce mod p_i again -- what g8_stage_residue_sum does, without the round trip through HBM
                 int32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                for (int q = 0; q < c.nparts; ++q) {
-                    const int x = (int)__ldcs(reinterpret_cast<const uint32_t *>(src + (size_t)i * pstride + (size_t)q * c.part_stride));
-                    a0 = __dp4a(x, 0x00000001, a0), a1 = __dp4a(x, 0x00000100, a1);
-                    a2 = __dp4a(x, 0x00010000, a2), a3 = __dp4a(x, 0x01000000, a3);
+                // constant trip count (PARTS, predicated) so that the loads of all shards -- and of the unrolled moduli --
+                // are in flight together
+                int x[PARTS > 0 ? PARTS : 1];
+#pragma unroll
+                for (int q = 0; q < PARTS; ++q)
+                    x[q] = (q < c.nparts) ? (int)__ldcs(reinterpret_cast<const uint32_t *>(src + (size_t)i * pstride + (size_t)q * c.part_stride)) : 0;
+#pragma unroll
+                for (int q = 0; q < PARTS; ++q) {
+                    a0 = __dp4a(x[q], 0x00000001, a0), a1 = __dp4a(x[q], 0x00000100, a1);
+                    a2 = __dp4a(x[q], 0x00010000, a2), a3 = __dp4a(x[q], 0x01000000, a3);
                 }
                 const int32_t p = g8d_moduli[INT8][i], pinv = g8d_pinv32[INT8][i];
                 a0 = mod_i32(a0, p, pinv), a1 = mod_i32(a1, p, pinv), a2 = mod_i32(a2, p, pinv), a3 = mod_i32(a3, p, pinv);
@@ -195,6 +202,15 @@ template <typename T, bool DD, int MODE> static void crt_go(const CrtArgs &c, co
     if (total == 0) return;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(c.C) % 16 == 0) && ((c.ldc * sizeof(T)) % 16 == 0);
     const unsigned grid = (unsigned)((total + 255) / 256);
+    if constexpr (!CrtTraits<T>::cplx) {
+        if (c.nparts > 1) { // K-sharded: per-shard residues summed inside the kernel (real types, INT8 backend; checked by the C ABI)
+            auto go = [&](auto kv, auto kn) { vec_ok ? kv<<<grid, 256, 0, st>>>(c, hs, groups, total) : kn<<<grid, 256, 0, st>>>(c, hs, groups, total); };
+            if (c.nparts <= 2) go(crt_kernel<T, DD, MODE, true, INT8, 2>, crt_kernel<T, DD, MODE, false, INT8, 2>);
+            else if (c.nparts <= 4) go(crt_kernel<T, DD, MODE, true, INT8, 4>, crt_kernel<T, DD, MODE, false, INT8, 4>);
+            else go(crt_kernel<T, DD, MODE, true, INT8, 8>, crt_kernel<T, DD, MODE, false, INT8, 8>);
+            return;
+        }
+    }
     if (c.backend == FP8) {
         if (vec_ok) crt_kernel<T, DD, MODE, true, FP8><<<grid, 256, 0, st>>>(c, hs, groups, total);
         else crt_kernel<T, DD, MODE, false, FP8><<<grid, 256, 0, st>>>(c, hs, groups, total);

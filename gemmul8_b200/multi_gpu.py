@@ -224,7 +224,8 @@ class KShardGemm:
         G = max(1, min(pipeline_groups, N))
         self.batches = [(i * N // G, (i + 1) * N // G - i * N // G) for i in range(G)]  # (first modulus, count)
         per = n * N * self.m_pad
-        self.C_mid = None if variant == "fused" else st.empty(N * self.nc * self.m_pad, torch.int8)  # [modulus][col][row]
+        # [modulus][col][row]; the fused variant with <= 4 shards lets the CRT kernel sum the shards and needs no C_mid
+        self.C_mid = None if (variant == "fused" and self.W <= 4) else st.empty(N * self.nc * self.m_pad, torch.int8)
         self.peers = None
         if variant == "fused":
             if self.nc % st.scatter_granularity:
@@ -337,8 +338,12 @@ class KShardGemm:
             self._rank_barrier()
             self._mark("barrier")
             r0 = self.rank * nc
-            # the CRT sums the per-shard residues itself (no separate sum pass, no C_mid round trip)
-            st.crt_parts(self.recv, W, N * nc * mp, mp, nc * mp, m, nc, C, m, self.sftA, self.sftB[r0:r0 + nc], alpha, beta)
+            if self.C_mid is None:
+                # the CRT sums the per-shard residues itself (no separate sum pass, no C_mid round trip): measured faster up to 4 shards
+                st.crt_parts(self.recv, W, N * nc * mp, mp, nc * mp, m, nc, C, m, self.sftA, self.sftB[r0:r0 + nc], alpha, beta)
+            else:
+                st.residue_sum(self.recv, W, N * nc * mp, mp, nc, mp, nc * mp, N, self.C_mid, mp, nc * mp)
+                st.crt(self.C_mid, mp, nc * mp, m, nc, C, m, self.sftA, self.sftB[r0:r0 + nc], alpha, beta)
             self._mark("sum+crt")
             return C
         pending = []  # (handle, batch) whose exchange is in flight
