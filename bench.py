@@ -173,6 +173,13 @@ def main():
         return 1
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        try:  # pin this rank to the CPUs next to its GPU before any pinned host buffer is allocated (first touch decides the NUMA node)
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        except Exception:
+            pass
     distributed = world > 1 and args.impl == "ours"
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

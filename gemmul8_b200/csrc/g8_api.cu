@@ -98,7 +98,6 @@ static int gemm_impl(const g8_gemm_desc &d, double *phase_ns) {
     if (d.dtype < F32 || d.dtype > C64 || d.op_A < 0 || d.op_A > 2 || d.op_B < 0 || d.op_B > 2) return G8_STATUS_INVALID_VALUE;
     if (d.num_moduli < 2 || d.num_moduli > G8_MAX_MODULI) return G8_STATUS_INVALID_VALUE;
     if (d.backend != INT8 && d.backend != FP8) return G8_STATUS_INVALID_VALUE;
-    if (d.backend == FP8 && d.dtype >= C32) return G8_STATUS_NOT_SUPPORTED; // complex FP8 (9 GEMMs per modulus) is not built yet
     if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
     if (d.m == 0 || d.n == 0) return 0;
 
@@ -154,7 +153,7 @@ static int gemm_impl(const g8_gemm_desc &d, double *phase_ns) {
             g.A = A_bound, g.B = B_bound, g.strideA = s.sizeA, g.strideB = s.sizeB;
             g.m = d.m, g.n = d.n, g.m_pad = s.m_pad, g.k_pad = s.k_pad;
             g.num_units = 1, g.first_modulus = 0;
-            g.epi = d.backend == FP8 ? EPI_F8_BOUND : (cplx ? EPI_BOUND_MAX_CPLX : EPI_BOUND_MAX);
+            g.epi = d.backend == FP8 ? (cplx ? EPI_F8_BOUND_CPLX : EPI_F8_BOUND) : (cplx ? EPI_BOUND_MAX_CPLX : EPI_BOUND_MAX);
             g.k_true = (int)d.k;
             g.groupA[0] = 0, g.groupA[1] = 1, g.groupA[2] = 2;
             g.groupB[0] = 0, g.groupB[1] = 1, g.groupB[2] = 2;
@@ -174,7 +173,29 @@ static int gemm_impl(const g8_gemm_desc &d, double *phase_ns) {
     tm.mark(1);
 
     // ---- stage 2: all moduli in one persistent tensor-core launch, mod-p fused ----
-    if (d.k != 0) {
+    if (d.k != 0 && d.backend == FP8 && cplx) {
+        // complex FP8 = 9 products per modulus (gemmul8_complex.hpp:163-190): the three 3M products ArBr, AiBi, (Ar+Ai)(Br+Bi) each go
+        // through the real FP8 kernel (3 piece products + recombination, residue mod p as int16) into scratch, then one combine pass.
+        // Scratch (the reference's C_hi area) holds 3 x int16 x m_pad x n per modulus: moduli are processed in batches that fit.
+        const size_t per_mod = 3 * sizeof(int16_t) * s.sizeC;
+        const unsigned batch = (unsigned)std::min<size_t>(N, scratch_avail / per_mod);
+        if (batch == 0) return G8_STATUS_NOT_SUPPORTED;
+        int16_t *prod = reinterpret_cast<int16_t *>(scratch);
+        for (unsigned u0 = 0; u0 < N; u0 += batch) {
+            const unsigned nu = std::min(batch, N - u0);
+            for (int q = 0; q < 3; ++q) {
+                GemmArgs g{};
+                g.A = A_lo, g.B = B_lo, g.strideA = s.sizeA, g.strideB = s.sizeB;
+                g.m = d.m, g.n = d.n, g.m_pad = s.m_pad, g.k_pad = s.k_pad;
+                g.num_units = (int)nu, g.first_modulus = (int)u0, g.epi = EPI_F8_MOD;
+                g.groupA[0] = q * (int)groupA_planes, g.groupB[0] = q * (int)groupB_planes;
+                g.out = prod + (size_t)q * nu * s.sizeC, g.out_stride = s.sizeC, g.ldc = s.m_pad;
+                if (int e = launch_gemm_tc(g, st)) return e;
+            }
+            launch_f8_cplx_combine(prod, prod + (size_t)nu * s.sizeC, prod + 2 * (size_t)nu * s.sizeC, s.sizeC, (int)nu, (int)u0,
+                                   reinterpret_cast<int16_t *>(C_mid) + 2 * (size_t)u0 * s.sizeC, st);
+        }
+    } else if (d.k != 0) {
         GemmArgs g{};
         g.A = A_lo, g.B = B_lo, g.strideA = s.sizeA, g.strideB = s.sizeB;
         g.m = d.m, g.n = d.n, g.m_pad = s.m_pad, g.k_pad = s.k_pad;
@@ -195,6 +216,37 @@ static int gemm_impl(const g8_gemm_desc &d, double *phase_ns) {
     tm.mark(4);
     tm.finish(phase_ns);
     return (int)cudaPeekAtLastError();
+}
+
+// ---- FP8 backend, complex types: 3M recombination of the per-product residues (conv_hi2mid_complex.hpp:130-188) ----
+// 8 consecutive elements per thread: three 128-bit loads, one 256-bit worth of {re, im} int16 pairs out.
+__global__ void __launch_bounds__(256) f8_cplx_combine_kernel(const int16_t *__restrict__ rr, const int16_t *__restrict__ ii, const int16_t *__restrict__ ss,
+                                                              size_t groups_per_unit, int first_modulus, int16_t *__restrict__ C_mid) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= groups_per_unit) return;
+    const int u     = blockIdx.y;
+    const int32_t p = g8d_moduli[FP8][first_modulus + u], pinv = g8d_pinv32[FP8][first_modulus + u];
+    const size_t e0 = ((size_t)u * groups_per_unit + i) * 8;
+    const uint4 a = *reinterpret_cast<const uint4 *>(rr + e0), b = *reinterpret_cast<const uint4 *>(ii + e0), c = *reinterpret_cast<const uint4 *>(ss + e0);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, cw[4] = {c.x, c.y, c.z, c.w};
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int sh     = (j & 1) * 16;
+        const int32_t x0 = (int32_t)(int16_t)(aw[j >> 1] >> sh), x1 = (int32_t)(int16_t)(bw[j >> 1] >> sh), x2 = (int32_t)(int16_t)(cw[j >> 1] >> sh);
+        const int32_t re = mod_i32(x0 - x1, p, pinv), im = mod_i32(x2 - x0 - x1, p, pinv);
+        o[j]             = (uint32_t)(re & 0xFFFF) | ((uint32_t)im << 16);
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(C_mid + e0 * 2);
+    dst[0]     = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1]     = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+void launch_f8_cplx_combine(const int16_t *rr, const int16_t *ii, const int16_t *ss, size_t elems_per_unit, int num_units, int first_modulus,
+                            int16_t *C_mid, cudaStream_t st) {
+    const size_t groups = elems_per_unit / 8; // m_pad * n, m_pad % 256 == 0
+    const dim3 grid((unsigned)((groups + 255) / 256), (unsigned)num_units);
+    f8_cplx_combine_kernel<<<grid, 256, 0, st>>>(rr, ii, ss, groups, first_modulus, C_mid);
 }
 
 // ---- K-sharded multi-GPU helpers (no reference counterpart; arithmetic = conv_hi2mid_real.hpp:19-22) ----

@@ -205,10 +205,11 @@ template <> struct EpiCfg<EPI_F8_BOUND>       { static constexpr int TILE_COL = 
 template <> struct EpiCfg<EPI_F8_RAW>         { static constexpr int TILE_COL = 256, NACC = 1, NCHAIN = 1; };
 template <> struct EpiCfg<EPI_MOD_I8_SCATTER> { static constexpr int TILE_COL = 256, NACC = 1, NCHAIN = 1; };
 template <> struct EpiCfg<EPI_RAW_I32_SCATTER> { static constexpr int TILE_COL = 256, NACC = 1, NCHAIN = 1; };
+template <> struct EpiCfg<EPI_F8_BOUND_CPLX>  { static constexpr int TILE_COL = 128, NACC = 2, NCHAIN = 2; };
 // EPI_MOD_I8_SCATTER staging: per epilogue warp 32 columns x (128 rows + 16 B pad); the pad makes the 16-byte shared stores of
 // the 32 lanes (one column each) bank-conflict free: 144 B stride = 36 banks -> lane l starts at bank 4l mod 32
 constexpr int SCAT_ROWS = 128, SCAT_PITCH = SCAT_ROWS + 16, SCAT_WARP_BYTES = 32 * SCAT_PITCH, SCAT_BYTES = 4 * SCAT_WARP_BYTES;
-template <int EPI> constexpr bool is_f8 = (EPI == EPI_F8_MOD || EPI == EPI_F8_BOUND || EPI == EPI_F8_RAW);
+template <int EPI> constexpr bool is_f8 = (EPI == EPI_F8_MOD || EPI == EPI_F8_BOUND || EPI == EPI_F8_RAW || EPI == EPI_F8_BOUND_CPLX);
 
 // CG = 1: one CTA per tile (128 columns of C x TILE_COL rows).  CG = 2: a CTA pair (tcgen05 cta_group::2) shares a
 // 256-column tile; each CTA stages its own 128 columns' operand plus HALF of the row-side operand, which halves the
@@ -271,7 +272,7 @@ __host__ __device__ __forceinline__ int f8_plane_base(int idx) { return idx < 6 
 template <int EPI> __device__ __forceinline__ void chain_groups(int acc, int c, int &ga, int &gb) {
     if constexpr (EPI == EPI_MOD_I8_CPLX) {
         ga = acc, gb = acc; // ArBr, AiBi, (Ar+Ai)(Br+Bi)
-    } else if constexpr (EPI == EPI_BOUND_MAX_CPLX) {
+    } else if constexpr (EPI == EPI_BOUND_MAX_CPLX || EPI == EPI_F8_BOUND_CPLX) {
         ga = c;                      // acc0 = |Ar||Br| + |Ai||Bi| ; acc1 = |Ar||Bi| + |Ai||Br|
         gb = (acc == 0) ? c : 1 - c;
     } else {
@@ -344,8 +345,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                             // square moduli: AhBl, AlBh, AlBl (gemmul8_real.hpp:159-170); otherwise Karatsuba hi*hi, lo*lo, sum*sum (:171-180)
                             const int idx = P.first_modulus + tc.unit, base = f8_plane_base(idx);
                             const bool sq = idx < 6;
-                            planeA = base + (sq ? (acc == 0 ? 0 : 1) : acc);
-                            planeB = base + (sq ? (acc == 1 ? 0 : 1) : acc);
+                            planeA = P.groupA[0] + base + (sq ? (acc == 0 ? 0 : 1) : acc); // group offset: 0 (real) or the Re / Im / Re+Im set
+                            planeB = P.groupB[0] + base + (sq ? (acc == 1 ? 0 : 1) : acc);
                         } else {
                             int ga, gb;
                             chain_groups<EPI>(acc, c, ga, gb);
@@ -643,6 +644,30 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                         *reinterpret_cast<uint4 *>(dst + c0 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
                     }
                 }
+            } else if constexpr (EPI == EPI_F8_BOUND_CPLX) {
+                // each accumulator summed 2k products in f32: inflate by (2k + 1) 2^-24 (the reference's bound chain, find_max.hpp:116-140,
+                // differs in shape -- three GEMMs and round-up additions -- but FP8 shifts are not a bit-parity contract)
+                const float ku2 = 2.0f * P.inflate;
+                int32_t cmax = 0;
+#pragma unroll 1
+                for (int c0 = 0; c0 < TILE_COL; c0 += 32) {
+                    int32_t v0[32], v1[32];
+                    tmem_ld32(taddr0 + c0, v0);
+                    tmem_ld32(ta1 + c0, v1);
+                    tmem_ld_wait();
+                    int32_t mine = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float f0 = __int_as_float(v0[j]), f1 = __int_as_float(v1[j]);
+                        const float u  = fmaxf(fmaxf(__fmaf_ru(ku2, f0, f0), __fmaf_ru(ku2, f1, f1)), 0.0f);
+                        const int32_t x = __float_as_int(u);
+                        cmax            = max(cmax, x);
+                        const int32_t r = __reduce_max_sync(0xffffffffu, x);
+                        mine            = (j == lane) ? r : mine;
+                    }
+                    if (mine > 0) atomicMax(&P.rowmax[row0 + c0 + lane], mine);
+                }
+                if (col_ok && cmax > 0) atomicMax(&P.colmax[col_c], cmax);
             } else { // EPI_BOUND_MAX_CPLX
                 int32_t cmax = 0;
 #pragma unroll 1
@@ -750,7 +775,7 @@ template <int EPI, int CG> static int launch_tc_cg(const GemmArgs &g, cudaStream
     using KS = KernelShape<EPI, CG>;
     int planes = g.num_units;
     for (int i = 0; i < 3; ++i) planes = max(planes, max(g.groupA[i], g.groupB[i]) + g.num_units);
-    if (EPI == EPI_F8_MOD) planes = f8_plane_base(g.first_modulus + g.num_units);
+    if (EPI == EPI_F8_MOD) planes = max(g.groupA[0], g.groupB[0]) + f8_plane_base(g.first_modulus + g.num_units);
     CUtensorMap mapL, mapC;
     if (!make_plane_map(&mapL, g.B, g.k_pad, g.n, planes, g.strideB, TILE_LANE)) return (int)cudaErrorNotSupported;
     if (!make_plane_map(&mapC, g.A, g.k_pad, g.m, planes, g.strideA, KS::TILE_COL / CG)) return (int)cudaErrorNotSupported;
@@ -807,6 +832,7 @@ int launch_gemm_tc(const GemmArgs &g, cudaStream_t st) {
     case EPI_F8_MOD: return launch_tc<EPI_F8_MOD>(g, st);
     case EPI_F8_BOUND: return launch_tc<EPI_F8_BOUND>(g, st);
     case EPI_F8_RAW: return launch_tc<EPI_F8_RAW>(g, st);
+    case EPI_F8_BOUND_CPLX: return launch_tc<EPI_F8_BOUND_CPLX>(g, st);
     }
     return (int)cudaErrorInvalidValue;
 }

@@ -43,6 +43,9 @@ enum GemmEpilogue : int {
     // into the owning rank's peer-mapped buffer.  Selected internally when GemmArgs::owner_cols != 0.
     EPI_MOD_I8_SCATTER = 8,
     EPI_RAW_I32_SCATTER = 9, // same for the raw INT32 partial (the bound product of accurate mode)
+    // FP8 backend, complex types: the residue planes of Re / Im / (Re+Im) go through EPI_F8_MOD once per 3M product (plane-group
+    // offsets groupA[0] / groupB[0]); the bound product needs its own epilogue
+    EPI_F8_BOUND_CPLX = 10, // max over max(up(|Ar||Br| + |Ai||Bi|), up(|Ar||Bi| + |Ai||Br|)), up(x) = fma_ru((2k+1) 2^-24, x, x)
 };
 
 struct GemmArgs {
@@ -90,5 +93,10 @@ struct CrtArgs {
     size_t part_stride;
 };
 int launch_crt(const CrtArgs &c, int dtype, cudaStream_t st);
+
+// FP8 backend, complex: C_mid[u] = {sym((rr - ii) mod p), sym((ss - rr - ii) mod p)} (int16 x 2) from the three per-product residue
+// arrays rr = ArBr, ii = AiBi, ss = (Ar+Ai)(Br+Bi) mod p written by EPI_F8_MOD (conv_hi2mid_complex.hpp:130-188)
+void launch_f8_cplx_combine(const int16_t *rr, const int16_t *ii, const int16_t *ss, size_t elems_per_unit, int num_units, int first_modulus,
+                            int16_t *C_mid, cudaStream_t st);
 
 } // namespace g8

@@ -256,16 +256,18 @@ __device__ __forceinline__ uint32_t fp8_of_int(int32_t v) { // |v| <= 16: exact 
 }
 __device__ __forceinline__ uint32_t pack4u(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return a | (b << 8) | (c << 16) | (d << 24); }
 
-template <bool LARGE, int NV>
-__device__ __forceinline__ void split_store_f8(const double (&x)[NV], int num_moduli, int8_t *base, size_t plane_stride, size_t off) {
+// REAL: x -> planes[0].  CPLX: (xr, xi) -> Re planes[0], Im planes[1], (Re + Im) mod p planes[2] (mod.hpp:315-355 for the third set)
+template <bool LARGE, int NV, bool CPLX>
+__device__ __forceinline__ void split_store_f8(const double (&x)[NV], const double (&xi)[NV], int num_moduli, int8_t *const (&planes)[3],
+                                               size_t plane_stride, size_t off) {
     constexpr int NW = NV / 4;
-    auto store = [&](int plane, const uint32_t (&w)[NW]) {
-        int8_t *dst = base + (size_t)plane * plane_stride + off;
-        if constexpr (NW == 4) *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-        else if constexpr (NW == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
-        else *reinterpret_cast<uint32_t *>(dst) = w[0];
-    };
-    auto emit = [&](int idx, const int32_t (&r)[NV]) {
+    auto emit = [&](int8_t *base, int idx, const int32_t (&r)[NV]) {
+        auto store = [&](int plane, const uint32_t (&w)[NW]) {
+            int8_t *dst = base + (size_t)plane * plane_stride + off;
+            if constexpr (NW == 4) *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+            else if constexpr (NW == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
+            else *reinterpret_cast<uint32_t *>(dst) = w[0];
+        };
         const int pbase = idx < 6 ? 2 * idx : 12 + 3 * (idx - 6);
         uint32_t hi[NV], lo[NV], sm[NV];
         if (idx < 6) {
@@ -300,25 +302,48 @@ __device__ __forceinline__ void split_store_f8(const double (&x)[NV], int num_mo
             store(pbase + 2, w);
         }
     };
-    if (num_moduli > 1) { // modulus index 1: p = 1024
-        int32_t r[NV];
+    // one modulus: residues of the real (and imaginary, and their sum) parts -> plane sets
+    auto emit_all = [&](int idx, const int32_t (&rr)[NV], const int32_t (&ri)[NV]) {
+        emit(planes[0], idx, rr);
+        if constexpr (CPLX) {
+            emit(planes[1], idx, ri);
+            const int32_t p = g8d_moduli[FP8][idx];
+            int32_t rs[NV];
 #pragma unroll
-        for (int j = 0; j < NV; ++j) r[j] = residue1024(x[j]);
-        emit(1, r);
+            for (int j = 0; j < NV; ++j) rs[j] = sym_wrap(rr[j] + ri[j], p);
+            emit(planes[2], idx, rs);
+        }
+    };
+    if (num_moduli > 1) { // modulus index 1: p = 1024
+        int32_t r[NV], ri[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            r[j] = residue1024(x[j]);
+            if constexpr (CPLX) ri[j] = residue1024(xi[j]);
+            else ri[j] = 0;
+        }
+        emit_all(1, r, ri);
     }
     const int ngroups = g8d_numGroups[FP8][num_moduli];
     for (int g = 0; g < ngroups; ++g) {
-        double rr[NV];
+        double rr[NV], rri[NV];
 #pragma unroll
-        for (int j = 0; j < NV; ++j) rr[j] = level1<LARGE, FP8>(x[j], g);
+        for (int j = 0; j < NV; ++j) {
+            rr[j] = level1<LARGE, FP8>(x[j], g);
+            if constexpr (CPLX) rri[j] = level1<LARGE, FP8>(xi[j], g);
+        }
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
             const int idx = g8d_grpMembers[FP8][g][t];
             if (idx >= 0 && idx < num_moduli) {
-                int32_t r[NV];
+                int32_t r[NV], ri[NV];
 #pragma unroll
-                for (int j = 0; j < NV; ++j) r[j] = level2<FP8>(rr[j], idx);
-                emit(idx, r);
+                for (int j = 0; j < NV; ++j) {
+                    r[j] = level2<FP8>(rr[j], idx);
+                    if constexpr (CPLX) ri[j] = level2<FP8>(rri[j], idx);
+                    else ri[j] = 0;
+                }
+                emit_all(idx, r, ri);
             }
         }
     }
@@ -340,23 +365,38 @@ __device__ __forceinline__ void emit_elements(const T (&v)[NV], int sft, const S
     using U             = typename Scalar<T>::U;
     constexpr bool CPLX = Scalar<T>::cplx;
     constexpr int NW    = NV / 4;
-    if constexpr (BE == FP8 && !CPLX) {
+    if constexpr (BE == FP8) {
         const RowScale scale = make_scale(sft);
-        if constexpr (MODE == 2) {
-            uint32_t w[NW];
-#pragma unroll
-            for (int q = 0; q < NW; ++q)
-                w[q] = pack4u(upper_bound_f8<U>(v[4 * q], scale.f1, scale.f2), upper_bound_f8<U>(v[4 * q + 1], scale.f1, scale.f2),
-                              upper_bound_f8<U>(v[4 * q + 2], scale.f1, scale.f2), upper_bound_f8<U>(v[4 * q + 3], scale.f1, scale.f2));
-            int8_t *dst = a.planes[0] + off;
+        auto st = [&](int8_t *dst, const uint32_t (&w)[NW]) {
             if constexpr (NW == 4) *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
             else if constexpr (NW == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
             else *reinterpret_cast<uint32_t *>(dst) = w[0];
-        } else {
-            double x[NV];
+        };
+        if constexpr (MODE == 2) {
+            // bound planes: |x| * 2^s0 rounded UP to e4m3; complex: |Re| -> planes[0], |Im| -> planes[1]
+            uint32_t w[NW], wi[NW];
 #pragma unroll
-            for (int j = 0; j < NV; ++j) x[j] = scaled_trunc<U>(v[j], scale);
-            split_store_f8<LARGE, NV>(x, a.num_moduli, a.planes[0], a.plane_stride, off);
+            for (int q = 0; q < NW; ++q) {
+                if constexpr (CPLX) {
+                    w[q]  = pack4u(upper_bound_f8<U>(v[4 * q].x, scale.f1, scale.f2), upper_bound_f8<U>(v[4 * q + 1].x, scale.f1, scale.f2),
+                                   upper_bound_f8<U>(v[4 * q + 2].x, scale.f1, scale.f2), upper_bound_f8<U>(v[4 * q + 3].x, scale.f1, scale.f2));
+                    wi[q] = pack4u(upper_bound_f8<U>(v[4 * q].y, scale.f1, scale.f2), upper_bound_f8<U>(v[4 * q + 1].y, scale.f1, scale.f2),
+                                   upper_bound_f8<U>(v[4 * q + 2].y, scale.f1, scale.f2), upper_bound_f8<U>(v[4 * q + 3].y, scale.f1, scale.f2));
+                } else {
+                    w[q] = pack4u(upper_bound_f8<U>(v[4 * q], scale.f1, scale.f2), upper_bound_f8<U>(v[4 * q + 1], scale.f1, scale.f2),
+                                  upper_bound_f8<U>(v[4 * q + 2], scale.f1, scale.f2), upper_bound_f8<U>(v[4 * q + 3], scale.f1, scale.f2));
+                }
+            }
+            st(a.planes[0] + off, w);
+            if constexpr (CPLX) st(a.planes[1] + off, wi);
+        } else {
+            double x[NV], xi[NV];
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                if constexpr (CPLX) x[j] = scaled_trunc<U>(v[j].x, scale), xi[j] = scaled_trunc<U>(v[j].y, scale);
+                else x[j] = scaled_trunc<U>(v[j], scale), xi[j] = 0.0;
+            }
+            split_store_f8<LARGE, NV, CPLX>(x, xi, a.num_moduli, a.planes, a.plane_stride, off);
         }
     } else if constexpr (MODE == 2) {
         uint32_t wr[NW], wi[NW];
@@ -606,9 +646,13 @@ template <typename T, int BE> static void split_typed(const SplitArgs &a, int mo
 // mode 0: split with stored shifts, 1: fast (shift + split), 2: accurate stage (i) (s0 + bound planes),
 // 3: bound planes with the stored s0 (no statistics pass)
 void launch_split(const SplitArgs &a, int dtype, int mode, cudaStream_t st) {
-    if (a.backend == FP8) { // real types only (checked by the caller)
-        if (dtype == F32) split_typed<float, FP8>(a, mode, st);
-        else split_typed<double, FP8>(a, mode, st);
+    if (a.backend == FP8) {
+        switch (dtype) {
+        case F32: split_typed<float, FP8>(a, mode, st); break;
+        case F64: split_typed<double, FP8>(a, mode, st); break;
+        case C32: split_typed<float2, FP8>(a, mode, st); break;
+        case C64: split_typed<double2, FP8>(a, mode, st); break;
+        }
         return;
     }
     switch (dtype) {

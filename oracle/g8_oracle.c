@@ -480,3 +480,75 @@ void g8o_crt16_f(const int16_t *C_mid, size_t ldmid, size_t strideC, size_t m, s
             }
         }
 }
+
+/* ---------------------------------------------------------------- FP8 backend, complex types
+ * gemmul8_complex.hpp:163-190 + conv_hi2mid_complex.hpp:130-188: per modulus the 3M products of the Re / Im / (Re+Im) residue
+ * planes, each assembled from FP8 pieces; mathematically C_mid = {sym(Re(ab) mod p), sym(Im(ab) mod p)} as int16 pairs. */
+void g8o_gemm_mod_i16_cplx(const int16_t *Ar, const int16_t *Ai, size_t strideA, const int16_t *Br, const int16_t *Bi, size_t strideB,
+                           size_t m, size_t n, size_t k_pad, const int32_t *moduli, int num_moduli, int16_t *C_mid, size_t ldc,
+                           size_t strideC) {
+    for (int i = 0; i < num_moduli; ++i)
+        for (size_t c = 0; c < n; ++c)
+            for (size_t r = 0; r < m; ++r) {
+                const int16_t *ar = Ar + (size_t)i * strideA + r * k_pad, *ai = Ai + (size_t)i * strideA + r * k_pad;
+                const int16_t *br = Br + (size_t)i * strideB + c * k_pad, *bi = Bi + (size_t)i * strideB + c * k_pad;
+                int64_t re = 0, im = 0;
+                for (size_t l = 0; l < k_pad; ++l) {
+                    re += (int64_t)ar[l] * br[l] - (int64_t)ai[l] * bi[l];
+                    im += (int64_t)ar[l] * bi[l] + (int64_t)ai[l] * br[l];
+                }
+                int16_t *o = C_mid + ((size_t)i * strideC + c * ldc + r) * 2;
+                o[0]       = (int16_t)sym_mod_i64(re, moduli[i]);
+                o[1]       = (int16_t)sym_mod_i64(im, moduli[i]);
+            }
+}
+
+/* complex CRT on int16 residue pairs: g8o_crt_z / g8o_crt_c with the 16-bit residue reader */
+void g8o_crt16_z(const int16_t *C_mid, size_t ldmid, size_t strideC, size_t m, size_t n, int num_moduli, int use_dd,
+                 const double *qPi1, const double *qPi2, const double *P, double invP, const int16_t *sftA,
+                 const int16_t *sftB, int mode, const double *alpha, const double *beta, double *C, size_t ldc) {
+    for (size_t c = 0; c < n; ++c)
+        for (size_t r = 0; r < m; ++r) {
+            const int16_t *src = C_mid + (c * ldmid + r) * 2;
+            double vr = crt_value16(src, strideC * 2, num_moduli, use_dd, qPi1, qPi2, P, invP);
+            double vi = crt_value16(src + 1, strideC * 2, num_moduli, use_dd, qPi1, qPi2, P, invP);
+            int s     = (int)sftA[r] + (int)sftB[c];
+            double xr = scalbn(vr, s), xi = scalbn(vi, s);
+            double *o = C + (c * ldc + r) * 2;
+            switch (mode) {
+            case 0: o[0] = xr; o[1] = xi; break;
+            case 1: o[0] += xr; o[1] += xi; break;
+            case 2: o[0] = -xr; o[1] = -xi; break;
+            case 3: o[0] -= xr; o[1] -= xi; break;
+            default: {
+                double ar = alpha[0], ai = alpha[1], br = beta[0], bi = beta[1], yr = o[0], yi = o[1];
+                o[0] = fma(-bi, yi, fma(br, yr, fma(-ai, xi, ar * xr)));
+                o[1] = fma(bi, yr, fma(br, yi, fma(ai, xr, ar * xi)));
+            }
+            }
+        }
+}
+void g8o_crt16_c(const int16_t *C_mid, size_t ldmid, size_t strideC, size_t m, size_t n, int num_moduli,
+                 const double *qPi1, const double *P, double invP, const int16_t *sftA, const int16_t *sftB, int mode,
+                 const float *alpha, const float *beta, float *C, size_t ldc) {
+    for (size_t c = 0; c < n; ++c)
+        for (size_t r = 0; r < m; ++r) {
+            const int16_t *src = C_mid + (c * ldmid + r) * 2;
+            double vr = crt_value16(src, strideC * 2, num_moduli, 0, qPi1, NULL, P, invP);
+            double vi = crt_value16(src + 1, strideC * 2, num_moduli, 0, qPi1, NULL, P, invP);
+            int s     = (int)sftA[r] + (int)sftB[c];
+            float xr = scalbnf((float)vr, s), xi = scalbnf((float)vi, s);
+            float *o = C + (c * ldc + r) * 2;
+            switch (mode) {
+            case 0: o[0] = xr; o[1] = xi; break;
+            case 1: o[0] += xr; o[1] += xi; break;
+            case 2: o[0] = -xr; o[1] = -xi; break;
+            case 3: o[0] -= xr; o[1] -= xi; break;
+            default: {
+                float ar = alpha[0], ai = alpha[1], br = beta[0], bi = beta[1], yr = o[0], yi = o[1];
+                o[0] = fmaf(-bi, yi, fmaf(br, yr, fmaf(-ai, xi, ar * xr)));
+                o[1] = fmaf(bi, yr, fmaf(br, yi, fmaf(ai, xr, ar * xi)));
+            }
+            }
+        }
+}

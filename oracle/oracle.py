@@ -263,13 +263,21 @@ def split(O: Operand, sft: np.ndarray, num_moduli: int, backend="INT8"):
     mod = np.array(T.moduli(backend)[:num_moduli], dtype=np.int32)
     sft = np.ascontiguousarray(sft, dtype=np.int16)
     out = []
-    if backend == "FP8":  # real types: int16 residues (the device stores each as 2-3 e4m3 pieces, see decode_fp8_planes)
-        pz = _real_parts(O.view)[0]
-        planes = np.zeros((num_moduli, O.rows, k_pad), dtype=np.int16)
-        fn = L.g8o_split16_f if pz.dtype == np.float32 else L.g8o_split16_d
-        fn(_p(pz), _sz(O.inner), 1, _sz(O.rows), _sz(O.inner), _sz(k_pad), _p(sft), _p(mod), int(num_moduli),
-           _p(planes), _sz(O.rows * k_pad))
-        return [planes]
+    if backend == "FP8":  # int16 residues (the device stores each as 2-3 e4m3 pieces, see decode_fp8_planes)
+        for pz in _real_parts(O.view):
+            planes = np.zeros((num_moduli, O.rows, k_pad), dtype=np.int16)
+            fn = L.g8o_split16_f if pz.dtype == np.float32 else L.g8o_split16_d
+            fn(_p(pz), _sz(O.inner), 1, _sz(O.rows), _sz(O.inner), _sz(k_pad), _p(sft), _p(mod), int(num_moduli),
+               _p(planes), _sz(O.rows * k_pad))
+            out.append(planes)
+        if len(out) == 2:  # complex: third plane set (Re + Im) mod p, symmetric
+            ssum = out[0].astype(np.int32) + out[1].astype(np.int32)
+            ri = np.empty_like(out[0])
+            for i, p in enumerate(mod):
+                h = p // 2
+                ri[i] = np.where(ssum[i] > h, ssum[i] - p, np.where(ssum[i] < -h, ssum[i] + p, ssum[i])).astype(np.int16)
+            out.append(ri)
+        return out
     for pz in _real_parts(O.view):
         planes = np.zeros((num_moduli, O.rows, k_pad), dtype=np.int8)
         fn = L.g8o_split_f if pz.dtype == np.float32 else L.g8o_split_d
@@ -293,6 +301,12 @@ def gemm_mod(A_lo, B_lo, m: int, n: int, num_moduli: int, backend="INT8"):
     mod = np.array(T.moduli(backend)[:num_moduli], dtype=np.int32)
     m_pad = pad256(m)
     k_pad = A_lo[0].shape[2]
+    if backend == "FP8" and len(A_lo) > 1:
+        C = np.zeros((num_moduli, n, m_pad, 2), dtype=np.int16)
+        L.g8o_gemm_mod_i16_cplx(_p(A_lo[0]), _p(A_lo[1]), _sz(A_lo[0].shape[1] * k_pad), _p(B_lo[0]), _p(B_lo[1]),
+                                _sz(B_lo[0].shape[1] * k_pad), _sz(m), _sz(n), _sz(k_pad), _p(mod), int(num_moduli),
+                                _p(C), _sz(m_pad), _sz(m_pad * n))
+        return C
     if backend == "FP8":
         C = np.zeros((num_moduli, n, m_pad), dtype=np.int16)
         L.g8o_gemm_mod_i16(_p(A_lo[0]), _sz(A_lo[0].shape[1] * k_pad), _p(B_lo[0]), _sz(B_lo[0].shape[1] * k_pad),
@@ -342,8 +356,17 @@ def crt(C_mid, m, n, num_moduli, sftA, sftB, dtype, alpha=1.0, beta=0.0, C0=None
     sftB = np.ascontiguousarray(sftB, dtype=np.int16)
     mode = 4 if device_scalars else _mode(alpha, beta)
     ldc = C.strides[1] // C.itemsize
+    if backend == "FP8" and cplx:
+        a = np.array([complex(alpha).real, complex(alpha).imag], dtype=np.float32 if f32 else np.float64)
+        b = np.array([complex(beta).real, complex(beta).imag], dtype=np.float32 if f32 else np.float64)
+        if f32:
+            L.g8o_crt16_c(_p(C_mid), _sz(m_pad), _sz(m_pad * n), _sz(m), _sz(n), int(num_moduli), _p(q1), _p(P),
+                          ctypes.c_double(invP), _p(sftA), _p(sftB), mode, _p(a), _p(b), _p(C), _sz(ldc))
+        else:
+            L.g8o_crt16_z(_p(C_mid), _sz(m_pad), _sz(m_pad * n), _sz(m), _sz(n), int(num_moduli), use_dd, _p(q1), _p(q2),
+                          _p(P), ctypes.c_double(invP), _p(sftA), _p(sftB), mode, _p(a), _p(b), _p(C), _sz(ldc))
+        return C
     if backend == "FP8":
-        assert not cplx
         if f32:
             L.g8o_crt16_f(_p(C_mid), _sz(m_pad), _sz(m_pad * n), _sz(m), _sz(n), int(num_moduli), _p(q1), _p(P),
                           ctypes.c_double(invP), _p(sftA), _p(sftB), mode, ctypes.c_float(alpha), ctypes.c_float(beta),

@@ -73,13 +73,16 @@ def read_workspace(work, m, n, k, num_moduli, cplx, enable_skip_scalA=False, ena
     L = api.layout(m, n, k, num_moduli, cplx, enable_skip_scalA, enable_skip_scalB, backend=backend)
     w = api.aligned_view(work).cpu().numpy()
     N, G = num_moduli, L.groups
-    if backend == 1:  # FP8 backend (real): num_mat e4m3 planes per operand, int16 C_mid
+    if backend == 1:  # FP8 backend: num_mat e4m3 planes per operand (x 3 plane sets Re / Im / Re+Im for complex), int16 C_mid
         from gemmul8_b200 import tables as T
         nm = T.num_mat("FP8", N)
         out = {"sftA": w[L.sftA:L.sftA + 2 * m].view(np.int16).copy(), "sftB": w[L.sftB:L.sftB + 2 * n].view(np.int16).copy()}
-        out["A_raw"] = w[L.A_lo:L.A_lo + L.sizeA * nm].reshape(nm, L.m_pad, L.k_pad)[:, :m].copy()
-        out["B_raw"] = w[L.B_lo:L.B_lo + L.sizeB * nm].reshape(nm, n, L.k_pad).copy()
-        out["C_mid"] = w[L.C_mid:L.C_mid + 2 * L.sizeC * N].view(np.int16).reshape(N, n, L.m_pad).copy()
+        rawA = w[L.A_lo:L.A_lo + L.sizeA * nm * G].reshape(G, nm, L.m_pad, L.k_pad)[:, :, :m]
+        rawB = w[L.B_lo:L.B_lo + L.sizeB * nm * G].reshape(G, nm, n, L.k_pad)
+        out["A_raw"], out["B_raw"] = rawA[0].copy(), rawB[0].copy()
+        out["A_raw_sets"], out["B_raw_sets"] = [rawA[g].copy() for g in range(G)], [rawB[g].copy() for g in range(G)]
+        cm = w[L.C_mid:L.C_mid + L.mid_bytes * L.sizeC * N].view(np.int16)
+        out["C_mid"] = cm.reshape(N, n, L.m_pad, 2).copy() if cplx else cm.reshape(N, n, L.m_pad).copy()
         out["layout"] = L
         return out
     nA = num_moduli + int(enable_skip_scalA)

@@ -142,6 +142,18 @@ def test_crt_stage_all_modes(env):
     assert not D.FAILS, D.FAILS
 
 
+def test_fp8_backend_vs_oracle(env):
+    """FP8 backend (gemmLt<T, FP8>, real AND complex types): e4m3 piece planes decode to the oracle's residues, C_mid and C are
+    bit-exact given the device's shifts (tools/gpu_debug.py:check_fp8)."""
+    import sys
+    sys.path.insert(0, str(ROOT / "tools"))
+    import gpu_debug as D
+
+    D.FAILS.clear()
+    D.check_fp8()
+    assert not D.FAILS, D.FAILS
+
+
 def test_full_size_properties(env):
     """BASELINE size (8192^3, N=14): size-independent checks -- linearity in alpha/beta is exact, permuting columns of B
     permutes columns of C bit for bit (column-wise shifts), and a 256x256 corner matches float64 numpy to emulated precision."""

@@ -141,3 +141,20 @@ def test_alpha_beta_modes():
     for a, b in ((1, 1), (-1, 0), (-1, 1), (0.5, 2.0)):
         r = O.emulate(A, B, num_moduli=14, alpha=a, beta=b, C0=C0)["C"]
         assert np.allclose(r, a * base + b * C0, rtol=1e-15, atol=1e-15)
+
+
+@pytest.mark.parametrize("dtype,N", [(np.complex128, 13), (np.complex64, 6), (np.float64, 12)])
+def test_oracle_fp8_backend_accuracy(dtype, N):
+    """FP8-backend restatement (16-bit residues, real and complex): fast mode reproduces the product to the emulated precision"""
+    from oracle import oracle as O
+    rng = np.random.default_rng(5)
+    m, n, k = 12, 9, 40
+    def rnd(s):
+        x = rng.standard_normal(s)
+        return (x + 1j * rng.standard_normal(s)).astype(dtype) if np.dtype(dtype).kind == "c" else x.astype(dtype)
+    A, B = rnd((m, k)), rnd((k, n))
+    r = O.emulate(A, B, "N", "N", N, True, backend="FP8")
+    wide = np.complex128 if np.dtype(dtype).kind == "c" else np.float64
+    ref = A.astype(wide) @ B.astype(wide)
+    err = np.abs(r["C"] - ref).max() / np.abs(ref).max()
+    assert err < 64 * np.finfo(np.dtype(dtype)).eps, err
