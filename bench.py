@@ -155,6 +155,25 @@ def cpu_baseline_oracle_port():
     return {"value": round(2 * m * n * k / t * 1e-12, 9), "unit": "TFLOPS", "cores": 1, "sample": f"oracle/g8_oracle.c emulated DGEMM {m}x{n}x{k} N=14"}
 
 
+def ncu_traffic_bytes(kernel_substr):
+    """DRAM bytes per launch of a kernel from the committed ncu summary (captured once per kernel change with `ncu --set full`)."""
+    import csv
+    f = ROOT / "profiles" / "r01e_ncu_full_fast_summary.csv"
+    if not f.exists():
+        return None
+    rows = list(csv.reader(f.open()))
+    hdr, units = rows[0], rows[1]
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    for r in rows[2:]:
+        if kernel_substr in r[0]:
+            tot = 0.0
+            for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i = hdr.index(m)
+                tot += float(r[i]) * scale.get(units[i], 1.0)
+            return int(tot)
+    return None
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     args = parse()
@@ -312,7 +331,9 @@ def main():
         roofline = {"bound": "tensor", "kernel": "gemm_i8_tc_kernel<EPI_MOD_I8> (tcgen05.mma kind::i8, all moduli in one launch)",
                     "achieved": round(ach, 1), "peak": round(2 * bf16, 1), "unit": "TOP/s (int8 dense; TFLOP/s-equivalent)",
                     "frac": round(ach / (2 * bf16), 4), "peak_source": which, "peak_nominal": 4500.0,
-                    "traffic": None, "kernel_ms": round(t_gemm * 1e3, 4), "ops_per_launch": ops}
+                    "traffic": ncu_traffic_bytes("gemm_i8_tc_kernel<0, 2>") if be == 0 and S == 8192 and N == 14 else None,
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel, ncu --set full capture profiles/r01e_ncu_full_fast_summary.csv",
+                    "kernel_ms": round(t_gemm * 1e3, 4), "ops_per_launch": ops}
     elif ref is not None:
         tm = (ctypes.c_double * 4)()
         ph = []
@@ -327,7 +348,12 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    launches_per_call = 5 if fast else 10
+    # our kernels per call -- single GPU: fast = stats, splitA, splitB(+stats), GEMM, CRT; accurate adds stats/bound planes x2, bound GEMM,
+    # 2 x finalize.  K-sharded (fused): stats x2, shift x2, [bound planes x2, bound GEMM+scatter, maxabs, finalize x2], split x2, GEMM+scatter, (sum,) CRT
+    if mg is None:
+        launches_per_call = 5 if fast else 10
+    else:
+        launches_per_call = (8 if fast else 14) + (1 if world > 4 else 0)
     out = {
         "metric": "emulated DGEMM TFLOPS @ N=8192 num_moduli=14; INT8 TC-pipe % of peak",
         "value": round(value, 2), "unit": "TFLOPS", "n_gpus": n_gpus, "steps": args.steps, "warmup": warmup,

@@ -12,7 +12,8 @@
 //     match the previous call on this handle and the corresponding SKIP switch is on        (hook.cu:81-108, 688-691)
 //   * m,n,k <= 0 -> SUCCESS; null A/B/C -> INVALID_VALUE; allocation failure -> ALLOC_FAILED  (hook.cu:616-617, 362-368)
 //   * stream switches on a handle are ordered with an event                                 (hook.cu:141-162)
-// Deviation: this build has no FP8 backend; GEMMUL8_BACKEND=FP8 therefore falls through to native cuBLAS.
+// GEMMUL8_BACKEND=FP8 routes to the FP8 (e4m3) emulation exactly like the reference (hook.cu:567-584); no cuBLASLt handle is
+// needed here because the contraction is ours.
 #include "../../include/gemmul8.hpp"
 #include "../../include/gemmul8_c.h"
 
@@ -78,7 +79,7 @@ Policy read_policy(const TypeInfo &t) {
     p.keepA      = env_flag("GEMMUL8_SKIP_SCALE_A");
     p.keepB      = env_flag("GEMMUL8_SKIP_SCALE_B");
     p.backend    = env_backend("GEMMUL8_BACKEND", false);
-    p.emulate    = p.num_moduli >= 2 && p.num_moduli <= t.max_moduli && p.backend == G8_BACKEND_INT8;
+    p.emulate    = p.num_moduli >= 2 && p.num_moduli <= t.max_moduli && (p.backend == G8_BACKEND_INT8 || p.backend == G8_BACKEND_FP8);
     return p;
 }
 

@@ -53,6 +53,11 @@ def test_ld_preload_hook_matches_native_cublas(binaries):
         for (name, x), (_, y) in zip(emu, native):
             tol = 2e-5 if name.startswith("sgemm") else (1e-9 if "FASTMODE_D" in extra else 1e-11)
             assert abs(x - y) <= tol * max(1.0, abs(y)), (name, x, y, extra)
+    # GEMMUL8_BACKEND=FP8 (hook.cu:567-584): e4m3 emulation, ~9.2 bits per modulus -> N = 13 / 6 reach the same accuracy class
+    emu, err = _run_hook(binaries, {"GEMMUL8_NUM_MOD_D": "13", "GEMMUL8_NUM_MOD_S": "6", "GEMMUL8_BACKEND": "FP8"}, True)
+    assert "failed" not in err, err
+    for (name, x), (_, y) in zip(emu, native):
+        assert abs(x - y) <= (2e-5 if name.startswith("sgemm") else 1e-10) * max(1.0, abs(y)), (name, x, y, "FP8")
     # out-of-range moduli count -> native path again (hook.cu:625-629)
     off, _ = _run_hook(binaries, {"GEMMUL8_NUM_MOD_D": "21", "GEMMUL8_NUM_MOD_S": "14"}, True)
     assert off == native
