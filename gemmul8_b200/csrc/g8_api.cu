@@ -173,27 +173,28 @@ static int gemm_impl(const g8_gemm_desc &d, double *phase_ns) {
     tm.mark(1);
 
     // ---- stage 2: all moduli in one persistent tensor-core launch, mod-p fused ----
-    if (d.k != 0 && d.backend == FP8 && cplx) {
-        // complex FP8 = 9 products per modulus (gemmul8_complex.hpp:163-190): the three 3M products ArBr, AiBi, (Ar+Ai)(Br+Bi) each go
-        // through the real FP8 kernel (3 piece products + recombination, residue mod p as int16) into scratch, then one combine pass.
-        // Scratch (the reference's C_hi area) holds 3 x int16 x m_pad x n per modulus: moduli are processed in batches that fit.
-        const size_t per_mod = 3 * sizeof(int16_t) * s.sizeC;
+    if (d.k != 0 && d.backend == FP8) {
+        // FP8: 3 piece products per modulus (9 for complex: x the three 3M products, gemmul8_real.hpp:159-180, gemmul8_complex.hpp:163-190).
+        // Every product runs as its own unit on full 256 x 256 tiles (one plane pair per unit: the INT8 kernel's operand re-use and L2
+        // footprint) and leaves its residue mod p as int16 in scratch; one combine pass per batch recombines them into C_mid.
+        // (A 3-accumulators-per-tile kernel, EPI_F8_MOD, avoids the scratch round trip but is limited to 128-row tiles and a 3x larger
+        // L2 working set: measured 1.85 vs 2.95 PFLOP/s for cuBLASLt -- see DESIGN.md.)
+        // Scratch (the reference's C_hi area) holds prods x int16 x m_pad x n per modulus: moduli are processed in batches that fit.
+        const int prods      = cplx ? 9 : 3;
+        const size_t per_mod = (size_t)prods * sizeof(int16_t) * s.sizeC;
         const unsigned batch = (unsigned)std::min<size_t>(N, scratch_avail / per_mod);
         if (batch == 0) return G8_STATUS_NOT_SUPPORTED;
         int16_t *prod = reinterpret_cast<int16_t *>(scratch);
         for (unsigned u0 = 0; u0 < N; u0 += batch) {
             const unsigned nu = std::min(batch, N - u0);
-            for (int q = 0; q < 3; ++q) {
-                GemmArgs g{};
-                g.A = A_lo, g.B = B_lo, g.strideA = s.sizeA, g.strideB = s.sizeB;
-                g.m = d.m, g.n = d.n, g.m_pad = s.m_pad, g.k_pad = s.k_pad;
-                g.num_units = (int)nu, g.first_modulus = (int)u0, g.epi = EPI_F8_MOD;
-                g.groupA[0] = q * (int)groupA_planes, g.groupB[0] = q * (int)groupB_planes;
-                g.out = prod + (size_t)q * nu * s.sizeC, g.out_stride = s.sizeC, g.ldc = s.m_pad;
-                if (int e = launch_gemm_tc(g, st)) return e;
-            }
-            launch_f8_cplx_combine(prod, prod + (size_t)nu * s.sizeC, prod + 2 * (size_t)nu * s.sizeC, s.sizeC, (int)nu, (int)u0,
-                                   reinterpret_cast<int16_t *>(C_mid) + 2 * (size_t)u0 * s.sizeC, st);
+            GemmArgs g{};
+            g.A = A_lo, g.B = B_lo, g.strideA = s.sizeA, g.strideB = s.sizeB;
+            g.m = d.m, g.n = d.n, g.m_pad = s.m_pad, g.k_pad = s.k_pad;
+            g.num_units = (int)nu * prods, g.first_modulus = (int)u0, g.epi = EPI_F8_PROD;
+            g.prods = prods, g.set_stride = (int)groupA_planes;
+            g.out = prod, g.out_stride = s.sizeC, g.ldc = s.m_pad;
+            if (int e = launch_gemm_tc(g, st)) return e;
+            launch_f8_combine(prod, cplx, s.sizeC, (int)nu, (int)u0, reinterpret_cast<int16_t *>(C_mid) + (cplx ? 2 : 1) * (size_t)u0 * s.sizeC, st);
         }
     } else if (d.k != 0) {
         GemmArgs g{};
@@ -218,35 +219,59 @@ static int gemm_impl(const g8_gemm_desc &d, double *phase_ns) {
     return (int)cudaPeekAtLastError();
 }
 
-// ---- FP8 backend, complex types: 3M recombination of the per-product residues (conv_hi2mid_complex.hpp:130-188) ----
-// 8 consecutive elements per thread: three 128-bit loads, one 256-bit worth of {re, im} int16 pairs out.
-__global__ void __launch_bounds__(256) f8_cplx_combine_kernel(const int16_t *__restrict__ rr, const int16_t *__restrict__ ii, const int16_t *__restrict__ ss,
-                                                              size_t groups_per_unit, int first_modulus, int16_t *__restrict__ C_mid) {
+// ---- FP8 backend: recombination of the per-product residues written by EPI_F8_PROD (mod.hpp:106-130, conv_hi2mid_complex.hpp:130-188) ----
+// prod layout: [modulus in batch][product (3 real / 9 complex)][m_pad * n] int16.  8 consecutive elements per thread, 128-bit accesses.
+__device__ __forceinline__ int32_t f8_recombine(int32_t c0, int32_t c1, int32_t c2, bool sq, int32_t sqrtp) {
+    return sq ? sqrtp * (c0 + c1) + c2 : (c0 * 256) + ((c2 - c0 - c1) * 16) + c1;
+}
+template <bool CPLX>
+__global__ void __launch_bounds__(256) f8_combine_kernel(const int16_t *__restrict__ prod, size_t elems_per_unit, int first_modulus, int16_t *__restrict__ C_mid) {
+    constexpr int NP = CPLX ? 9 : 3;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= groups_per_unit) return;
-    const int u     = blockIdx.y;
-    const int32_t p = g8d_moduli[FP8][first_modulus + u], pinv = g8d_pinv32[FP8][first_modulus + u];
-    const size_t e0 = ((size_t)u * groups_per_unit + i) * 8;
-    const uint4 a = *reinterpret_cast<const uint4 *>(rr + e0), b = *reinterpret_cast<const uint4 *>(ii + e0), c = *reinterpret_cast<const uint4 *>(ss + e0);
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, cw[4] = {c.x, c.y, c.z, c.w};
-    uint32_t o[8];
+    if (i * 8 >= elems_per_unit) return;
+    const int u = blockIdx.y, midx = first_modulus + u;
+    const int32_t p = g8d_moduli[FP8][midx], pinv = g8d_pinv32[FP8][midx];
+    const bool sq = midx < 6;
+    const int32_t sqrtp = sq ? g8d_f8sqrt[midx] : 0;
+    const int16_t *src = prod + (size_t)u * NP * elems_per_unit + i * 8;
+    uint32_t w[NP][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int sh     = (j & 1) * 16;
-        const int32_t x0 = (int32_t)(int16_t)(aw[j >> 1] >> sh), x1 = (int32_t)(int16_t)(bw[j >> 1] >> sh), x2 = (int32_t)(int16_t)(cw[j >> 1] >> sh);
-        const int32_t re = mod_i32(x0 - x1, p, pinv), im = mod_i32(x2 - x0 - x1, p, pinv);
-        o[j]             = (uint32_t)(re & 0xFFFF) | ((uint32_t)im << 16);
+    for (int q = 0; q < NP; ++q) {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(src + (size_t)q * elems_per_unit));
+        w[q][0] = v.x, w[q][1] = v.y, w[q][2] = v.z, w[q][3] = v.w;
     }
-    uint4 *dst = reinterpret_cast<uint4 *>(C_mid + e0 * 2);
-    dst[0]     = make_uint4(o[0], o[1], o[2], o[3]);
-    dst[1]     = make_uint4(o[4], o[5], o[6], o[7]);
+    auto get = [&](int q, int j) { return (int32_t)(int16_t)(w[q][j >> 1] >> ((j & 1) * 16)); };
+    if constexpr (!CPLX) {
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            const int32_t a = mod_i32(f8_recombine(get(0, j), get(1, j), get(2, j), sq, sqrtp), p, pinv);
+            const int32_t b = mod_i32(f8_recombine(get(0, j + 1), get(1, j + 1), get(2, j + 1), sq, sqrtp), p, pinv);
+            o[j >> 1]       = (uint32_t)(a & 0xFFFF) | ((uint32_t)b << 16);
+        }
+        *reinterpret_cast<uint4 *>(C_mid + (size_t)u * elems_per_unit + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+        uint32_t o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            // every 3M product is first reduced mod p (the recombined value is < 2^21, the differences stay far below 2^31)
+            const int32_t rr = mod_i32(f8_recombine(get(0, j), get(1, j), get(2, j), sq, sqrtp), p, pinv);
+            const int32_t ii = mod_i32(f8_recombine(get(3, j), get(4, j), get(5, j), sq, sqrtp), p, pinv);
+            const int32_t ss = mod_i32(f8_recombine(get(6, j), get(7, j), get(8, j), sq, sqrtp), p, pinv);
+            const int32_t re = mod_i32(rr - ii, p, pinv), im = mod_i32(ss - rr - ii, p, pinv);
+            o[j]             = (uint32_t)(re & 0xFFFF) | ((uint32_t)im << 16);
+        }
+        uint4 *dst = reinterpret_cast<uint4 *>(C_mid + ((size_t)u * elems_per_unit + i * 8) * 2);
+        dst[0]     = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1]     = make_uint4(o[4], o[5], o[6], o[7]);
+    }
 }
 
-void launch_f8_cplx_combine(const int16_t *rr, const int16_t *ii, const int16_t *ss, size_t elems_per_unit, int num_units, int first_modulus,
-                            int16_t *C_mid, cudaStream_t st) {
+void launch_f8_combine(const int16_t *prod, bool cplx, size_t elems_per_unit, int num_units, int first_modulus, int16_t *C_mid, cudaStream_t st) {
     const size_t groups = elems_per_unit / 8; // m_pad * n, m_pad % 256 == 0
     const dim3 grid((unsigned)((groups + 255) / 256), (unsigned)num_units);
-    f8_cplx_combine_kernel<<<grid, 256, 0, st>>>(rr, ii, ss, groups, first_modulus, C_mid);
+    if (cplx) f8_combine_kernel<true><<<grid, 256, 0, st>>>(prod, elems_per_unit, first_modulus, C_mid);
+    else f8_combine_kernel<false><<<grid, 256, 0, st>>>(prod, elems_per_unit, first_modulus, C_mid);
 }
 
 // ---- K-sharded multi-GPU helpers (no reference counterpart; arithmetic = conv_hi2mid_real.hpp:19-22) ----

@@ -206,10 +206,11 @@ template <> struct EpiCfg<EPI_F8_RAW>         { static constexpr int TILE_COL = 
 template <> struct EpiCfg<EPI_MOD_I8_SCATTER> { static constexpr int TILE_COL = 256, NACC = 1, NCHAIN = 1; };
 template <> struct EpiCfg<EPI_RAW_I32_SCATTER> { static constexpr int TILE_COL = 256, NACC = 1, NCHAIN = 1; };
 template <> struct EpiCfg<EPI_F8_BOUND_CPLX>  { static constexpr int TILE_COL = 128, NACC = 2, NCHAIN = 2; };
+template <> struct EpiCfg<EPI_F8_PROD>        { static constexpr int TILE_COL = 256, NACC = 1, NCHAIN = 1; };
 // EPI_MOD_I8_SCATTER staging: per epilogue warp 32 columns x (128 rows + 16 B pad); the pad makes the 16-byte shared stores of
 // the 32 lanes (one column each) bank-conflict free: 144 B stride = 36 banks -> lane l starts at bank 4l mod 32
 constexpr int SCAT_ROWS = 128, SCAT_PITCH = SCAT_ROWS + 16, SCAT_WARP_BYTES = 32 * SCAT_PITCH, SCAT_BYTES = 4 * SCAT_WARP_BYTES;
-template <int EPI> constexpr bool is_f8 = (EPI == EPI_F8_MOD || EPI == EPI_F8_BOUND || EPI == EPI_F8_RAW || EPI == EPI_F8_BOUND_CPLX);
+template <int EPI> constexpr bool is_f8 = (EPI == EPI_F8_MOD || EPI == EPI_F8_BOUND || EPI == EPI_F8_RAW || EPI == EPI_F8_BOUND_CPLX || EPI == EPI_F8_PROD);
 
 // CG = 1: one CTA per tile (128 columns of C x TILE_COL rows).  CG = 2: a CTA pair (tcgen05 cta_group::2) shares a
 // 256-column tile; each CTA stages its own 128 columns' operand plus HALF of the row-side operand, which halves the
@@ -262,6 +263,7 @@ struct KParams {
     // peer_out[o] (a peer-mapped buffer of rank o, or our own), at column (c - o * owner_cols).  owner_cols == 0: plain output `out`.
     void *peer_out[G8_MAX_PEERS];
     int owner_cols;
+    int prods, set_stride; // EPI_F8_PROD
     int tl_rot; // rotation of the lane-tile sweep so that the ranks do not all target the same owner at the same time
 };
 
@@ -341,7 +343,14 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                 for (int acc = 0; acc < EC::NACC; ++acc)
                     for (int c = 0; c < EC::NCHAIN; ++c) {
                         int planeA, planeB;
-                        if constexpr (EPI == EPI_F8_MOD) {
+                        if constexpr (EPI == EPI_F8_PROD) {
+                            // unit -> (modulus, product); product q = 3 * (plane set: Re, Im, Re+Im) + piece product
+                            const int idx = P.first_modulus + tc.unit / P.prods, q = tc.unit % P.prods;
+                            const int set = q / 3, a = q - 3 * set, base = f8_plane_base(idx) + set * P.set_stride;
+                            const bool sq = idx < 6;
+                            planeA = base + (sq ? (a == 0 ? 0 : 1) : a);
+                            planeB = base + (sq ? (a == 1 ? 0 : 1) : a);
+                        } else if constexpr (EPI == EPI_F8_MOD) {
                             // square moduli: AhBl, AlBh, AlBl (gemmul8_real.hpp:159-170); otherwise Karatsuba hi*hi, lo*lo, sum*sum (:171-180)
                             const int idx = P.first_modulus + tc.unit, base = f8_plane_base(idx);
                             const bool sq = idx < 6;
@@ -611,6 +620,28 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                     if (mine > 0) atomicMax(&P.rowmax[row0 + c0 + lane], mine);
                 }
                 if (col_ok && cmax > 0) atomicMax(&P.colmax[col_c], cmax);
+            } else if constexpr (EPI == EPI_F8_PROD) {
+                // c = float2int_rn(acc) (exact small-integer sum), reduced once: r = c - p * mulhi(c, floor(2^32/p)) in (-p/2, 3p/2)
+                const int pidx  = P.first_modulus + tc.unit / P.prods;
+                const int32_t p = g8d_moduli[FP8][pidx], pinv = g8d_pinv32[FP8][pidx];
+                int16_t *dst = reinterpret_cast<int16_t *>(P.out) + (size_t)tc.unit * P.out_stride + (size_t)col_c * P.ldc + row0;
+#pragma unroll 1
+                for (int c0 = 0; c0 < TILE_COL; c0 += 32) {
+                    int32_t v[32];
+                    tmem_ld32(taddr0 + c0, v);
+                    tmem_ld_wait();
+                    uint32_t w[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int32_t c0i = __float2int_rn(__int_as_float(v[2 * j])), c1i = __float2int_rn(__int_as_float(v[2 * j + 1]));
+                        const int32_t r0 = c0i - p * __mulhi(c0i, pinv), r1 = c1i - p * __mulhi(c1i, pinv);
+                        w[j] = (uint32_t)(r0 & 0xFFFF) | ((uint32_t)r1 << 16);
+                    }
+                    if (col_ok) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4 *>(dst + c0 + 8 * j) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+                    }
+                }
             } else if constexpr (EPI == EPI_F8_MOD) {
                 // mod.hpp:106-130: c_j = float2int_rn(acc_j); square moduli: sqrt(p)*(c0 + c1) + c2, else 256*c0 + 16*(c2 - c0 - c1) + c1; mod p
                 const int32_t p = g8d_moduli[FP8][midx], pinv = g8d_pinv32[FP8][midx];
@@ -776,6 +807,7 @@ template <int EPI, int CG> static int launch_tc_cg(const GemmArgs &g, cudaStream
     int planes = g.num_units;
     for (int i = 0; i < 3; ++i) planes = max(planes, max(g.groupA[i], g.groupB[i]) + g.num_units);
     if (EPI == EPI_F8_MOD) planes = max(g.groupA[0], g.groupB[0]) + f8_plane_base(g.first_modulus + g.num_units);
+    if (EPI == EPI_F8_PROD) planes = (g.prods / 3 - 1) * g.set_stride + f8_plane_base(g.first_modulus + (g.num_units + g.prods - 1) / g.prods);
     CUtensorMap mapL, mapC;
     if (!make_plane_map(&mapL, g.B, g.k_pad, g.n, planes, g.strideB, TILE_LANE)) return (int)cudaErrorNotSupported;
     if (!make_plane_map(&mapC, g.A, g.k_pad, g.m, planes, g.strideA, KS::TILE_COL / CG)) return (int)cudaErrorNotSupported;
@@ -792,6 +824,7 @@ template <int EPI, int CG> static int launch_tc_cg(const GemmArgs &g, cudaStream
     P.rowmax = g.rowmax, P.colmax = g.colmax;
     P.inflate = (float)(g.k_true + 1) * 0x1p-24f;
     P.owner_cols = 0, P.tl_rot = 0;
+    P.prods = g.prods > 0 ? g.prods : 3, P.set_stride = g.set_stride;
     if (g.owner_cols) {
         // the scatter is tile-granular: every lane tile (TILE_LANE * CG columns) must fall inside one owner's slab
         if (g.owner_cols % (TILE_LANE * CG) || (EPI != EPI_MOD_I8_SCATTER && EPI != EPI_RAW_I32_SCATTER)) return (int)cudaErrorInvalidValue;
@@ -833,6 +866,7 @@ int launch_gemm_tc(const GemmArgs &g, cudaStream_t st) {
     case EPI_F8_BOUND: return launch_tc<EPI_F8_BOUND>(g, st);
     case EPI_F8_RAW: return launch_tc<EPI_F8_RAW>(g, st);
     case EPI_F8_BOUND_CPLX: return launch_tc<EPI_F8_BOUND_CPLX>(g, st);
+    case EPI_F8_PROD: return launch_tc<EPI_F8_PROD>(g, st);
     }
     return (int)cudaErrorInvalidValue;
 }

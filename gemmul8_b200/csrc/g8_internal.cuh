@@ -46,6 +46,10 @@ enum GemmEpilogue : int {
     // FP8 backend, complex types: the residue planes of Re / Im / (Re+Im) go through EPI_F8_MOD once per 3M product (plane-group
     // offsets groupA[0] / groupB[0]); the bound product needs its own epilogue
     EPI_F8_BOUND_CPLX = 10, // max over max(up(|Ar||Br| + |Ai||Bi|), up(|Ar||Bi| + |Ai||Br|)), up(x) = fma_ru((2k+1) 2^-24, x, x)
+    // FP8 backend, the product path: ONE piece product per unit on a full 256 x 256 tile (same operand re-use and L2 footprint as the
+    // INT8 kernel); unit u -> modulus first_modulus + u / prods, product u % prods (3 piece products, x 3 plane sets for complex).
+    // Output: the product's residue mod p (not wrapped) as int16; launch_f8_combine recombines (mod.hpp:106-130).
+    EPI_F8_PROD = 11,
 };
 
 struct GemmArgs {
@@ -69,6 +73,8 @@ struct GemmArgs {
     void *peer_out[G8_MAX_PEERS];
     size_t owner_cols; // 0 = plain single-buffer output
     int rank, world;
+    // EPI_F8_PROD: products per modulus (3 real / 9 complex) and planes between the Re / Im / Re+Im plane sets
+    int prods, set_stride;
 };
 // tcgen05 path (product).  Returns cudaError_t-compatible int.
 int launch_gemm_tc(const GemmArgs &g, cudaStream_t st);
@@ -94,9 +100,9 @@ struct CrtArgs {
 };
 int launch_crt(const CrtArgs &c, int dtype, cudaStream_t st);
 
-// FP8 backend, complex: C_mid[u] = {sym((rr - ii) mod p), sym((ss - rr - ii) mod p)} (int16 x 2) from the three per-product residue
-// arrays rr = ArBr, ii = AiBi, ss = (Ar+Ai)(Br+Bi) mod p written by EPI_F8_MOD (conv_hi2mid_complex.hpp:130-188)
-void launch_f8_cplx_combine(const int16_t *rr, const int16_t *ii, const int16_t *ss, size_t elems_per_unit, int num_units, int first_modulus,
-                            int16_t *C_mid, cudaStream_t st);
+// FP8 backend: recombination of the per-product residues written by EPI_F8_PROD, laid out [modulus in batch][product][m_pad * n]:
+// real (3 products): C_mid[u] = sym(recombine(c0, c1, c2) mod p) (mod.hpp:106-130);  complex (9 products): the same per 3M product,
+// then {sym((rr - ii) mod p), sym((ss - rr - ii) mod p)} (conv_hi2mid_complex.hpp:130-188).  Output int16 (x 2 for complex).
+void launch_f8_combine(const int16_t *prod, bool cplx, size_t elems_per_unit, int num_units, int first_modulus, int16_t *C_mid, cudaStream_t st);
 
 } // namespace g8

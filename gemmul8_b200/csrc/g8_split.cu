@@ -269,36 +269,49 @@ __device__ __forceinline__ void split_store_f8(const double (&x)[NV], const doub
             else *reinterpret_cast<uint32_t *>(dst) = w[0];
         };
         const int pbase = idx < 6 ? 2 * idx : 12 + 3 * (idx - 6);
-        uint32_t hi[NV], lo[NV], sm[NV];
+        // All piece arithmetic runs on the FMA pipe: int -> float by the 1.5 * 2^23 magic constant, rounding by adding / subtracting
+        // it, and ONE packed F2FP per two pieces.  (I2F / F2I / FRND / single-value F2FP all issue on the quarter-rate conversion
+        // pipe, which bounded this kernel.)  Every value involved is an integer or a multiple of 1/64 below 2^10: exact in binary32.
+        constexpr float kMagicF = 12582912.0f; // 1.5 * 2^23
+        float af[NV], hf[NV], lf[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) af[j] = __fsub_rn(__int_as_float(0x4B400000 + r[j]), kMagicF); // exact: |r| < 2^22
         if (idx < 6) {
             const float sq = (float)g8d_f8sqrt[idx], inv = __fdiv_rn(1.0f, sq);
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
-                const float af = (float)r[j];
-                const float h  = rintf(__fmul_rn(af, inv));
-                const float l  = __fmaf_rn(-sq, h, af);
-                hi[j] = fp8_of_int((int32_t)h), lo[j] = fp8_of_int((int32_t)l);
+                hf[j] = __fsub_rn(__fadd_rn(__fmul_rn(af[j], inv), kMagicF), kMagicF); // rintf(af * inv): round-to-nearest-even like rintf
+                lf[j] = __fmaf_rn(-sq, hf[j], af[j]);
             }
         } else {
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
-                const int32_t a = r[j], s = a >> 31;
-                const int32_t q = ((a ^ s) - s + 15) >> 4;   // ceil(|a| / 16)
-                const int32_t h = (q ^ s) - s;               // sign(a) * q
-                const int32_t l = a - 16 * h;
-                hi[j] = fp8_of_int(h), lo[j] = fp8_of_int(l), sm[j] = fp8_of_int(h + l);
+                // h = sign(a) * ceil(|a| / 16) = sign(a) * floor((|a| + 15) / 16); (|a| + 15) / 16 is a multiple of 1/16, so
+                // floor(y) = rint(y - 15/32)
+                const float y  = __fmaf_rn(fabsf(af[j]), 0.0625f, 0.9375f - 0.46875f);
+                const float hm = __fsub_rn(__fadd_rn(y, kMagicF), kMagicF);
+                hf[j]          = copysignf(hm, af[j]);
+                lf[j]          = __fmaf_rn(-16.0f, hf[j], af[j]);
             }
         }
+        auto pack8 = [&](const float (&v)[NV], uint32_t (&w)[NW]) {
+#pragma unroll
+            for (int q = 0; q < NW; ++q) {
+                const uint32_t a = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(v[4 * q], v[4 * q + 1]), __NV_SATFINITE, __NV_E4M3);
+                const uint32_t b = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(v[4 * q + 2], v[4 * q + 3]), __NV_SATFINITE, __NV_E4M3);
+                w[q]             = a | (b << 16);
+            }
+        };
         uint32_t w[NW];
-#pragma unroll
-        for (int q = 0; q < NW; ++q) w[q] = pack4u(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+        pack8(hf, w);
         store(pbase, w);
-#pragma unroll
-        for (int q = 0; q < NW; ++q) w[q] = pack4u(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+        pack8(lf, w);
         store(pbase + 1, w);
         if (idx >= 6) {
+            float sf[NV];
 #pragma unroll
-            for (int q = 0; q < NW; ++q) w[q] = pack4u(sm[4 * q], sm[4 * q + 1], sm[4 * q + 2], sm[4 * q + 3]);
+            for (int j = 0; j < NV; ++j) sf[j] = __fadd_rn(hf[j], lf[j]);
+            pack8(sf, w);
             store(pbase + 2, w);
         }
     };
