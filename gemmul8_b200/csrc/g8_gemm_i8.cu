@@ -356,6 +356,11 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                             const bool sq = idx < 6;
                             planeA = P.groupA[0] + base + (sq ? (acc == 0 ? 0 : 1) : acc); // group offset: 0 (real) or the Re / Im / Re+Im set
                             planeB = P.groupB[0] + base + (sq ? (acc == 1 ? 0 : 1) : acc);
+                        } else if constexpr (EPI == EPI_MOD_I8) {
+                            // real: one product per modulus.  complex (prods = 3): unit -> (modulus, 3M product q) with the plane sets
+                            // Re / Im / Re+Im of BOTH operands selected by q
+                            const int q = tc.unit % P.prods, mu = tc.unit / P.prods;
+                            planeA = P.groupA[q] + mu, planeB = P.groupB[q] + mu;
                         } else {
                             int ga, gb;
                             chain_groups<EPI>(acc, c, ga, gb);
@@ -446,7 +451,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
             const int col_c   = tc.tl * (TILE_LANE * CG) + (int)rank * TILE_LANE + q * 32 + lane; // column of C owned by this thread
             const int row0    = tc.tc * TILE_COL;                  // first row of C of this tile
             const bool col_ok = col_c < P.n;
-            const int midx    = P.first_modulus + tc.unit;
+            const int midx    = P.first_modulus + ((EPI == EPI_MOD_I8) ? tc.unit / P.prods : tc.unit);
             // output base and column index inside it (peer scatter: the whole 256-column tile belongs to one owner)
             char *out_base = static_cast<char *>(P.out);
             int col_o      = col_c;
@@ -805,7 +810,8 @@ static int cta_group_pref() {
 template <int EPI, int CG> static int launch_tc_cg(const GemmArgs &g, cudaStream_t st) {
     using KS = KernelShape<EPI, CG>;
     int planes = g.num_units;
-    for (int i = 0; i < 3; ++i) planes = max(planes, max(g.groupA[i], g.groupB[i]) + g.num_units);
+    const int mods = (EPI == EPI_MOD_I8 && g.prods > 1) ? (g.num_units + g.prods - 1) / g.prods : g.num_units;
+    for (int i = 0; i < 3; ++i) planes = max(planes, max(g.groupA[i], g.groupB[i]) + mods);
     if (EPI == EPI_F8_MOD) planes = max(g.groupA[0], g.groupB[0]) + f8_plane_base(g.first_modulus + g.num_units);
     if (EPI == EPI_F8_PROD) planes = (g.prods / 3 - 1) * g.set_stride + f8_plane_base(g.first_modulus + (g.num_units + g.prods - 1) / g.prods);
     CUtensorMap mapL, mapC;
@@ -824,7 +830,7 @@ template <int EPI, int CG> static int launch_tc_cg(const GemmArgs &g, cudaStream
     P.rowmax = g.rowmax, P.colmax = g.colmax;
     P.inflate = (float)(g.k_true + 1) * 0x1p-24f;
     P.owner_cols = 0, P.tl_rot = 0;
-    P.prods = g.prods > 0 ? g.prods : 3, P.set_stride = g.set_stride;
+    P.prods = g.prods > 0 ? g.prods : (EPI == EPI_F8_PROD ? 3 : 1), P.set_stride = g.set_stride;
     if (g.owner_cols) {
         // the scatter is tile-granular: every lane tile (TILE_LANE * CG columns) must fall inside one owner's slab
         if (g.owner_cols % (TILE_LANE * CG) || (EPI != EPI_MOD_I8_SCATTER && EPI != EPI_RAW_I32_SCATTER)) return (int)cudaErrorInvalidValue;

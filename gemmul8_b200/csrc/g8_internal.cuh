@@ -73,7 +73,8 @@ struct GemmArgs {
     void *peer_out[G8_MAX_PEERS];
     size_t owner_cols; // 0 = plain single-buffer output
     int rank, world;
-    // EPI_F8_PROD: products per modulus (3 real / 9 complex) and planes between the Re / Im / Re+Im plane sets
+    // EPI_F8_PROD: products per modulus (3 real / 9 complex) and planes between the Re / Im / Re+Im plane sets;
+    // EPI_MOD_I8: prods = 3 runs the three 3M products of a complex modulus as separate units (plane sets from groupA / groupB)
     int prods, set_stride;
 };
 // tcgen05 path (product).  Returns cudaError_t-compatible int.
@@ -103,6 +104,9 @@ int launch_crt(const CrtArgs &c, int dtype, cudaStream_t st);
 // FP8 backend: recombination of the per-product residues written by EPI_F8_PROD, laid out [modulus in batch][product][m_pad * n]:
 // real (3 products): C_mid[u] = sym(recombine(c0, c1, c2) mod p) (mod.hpp:106-130);  complex (9 products): the same per 3M product,
 // then {sym((rr - ii) mod p), sym((ss - rr - ii) mod p)} (conv_hi2mid_complex.hpp:130-188).  Output int16 (x 2 for complex).
+// INT8 backend, complex: {re, im} = {sym((rr - ii) mod p), sym((ss - rr - ii) mod p)} (int8 x 2) from the three per-product residue
+// arrays [modulus in batch][rr, ii, ss][m_pad * n] written by EPI_MOD_I8 with prods = 3 (conv_hi2mid_complex.hpp:46-127)
+void launch_i8_cplx_combine(const int8_t *prod, size_t elems_per_unit, int num_units, int first_modulus, int8_t *C_mid, cudaStream_t st);
 void launch_f8_combine(const int16_t *prod, bool cplx, size_t elems_per_unit, int num_units, int first_modulus, int16_t *C_mid, cudaStream_t st);
 
 } // namespace g8
