@@ -158,7 +158,7 @@ def cpu_baseline_oracle_port():
 def ncu_traffic_bytes(kernel_substr):
     """DRAM bytes per launch of a kernel from the committed ncu summary (captured once per kernel change with `ncu --set full`)."""
     import csv
-    f = ROOT / "profiles" / "r01e_ncu_full_fast_summary.csv"
+    f = ROOT / "profiles" / "r01f_ncu_full_fast_summary.csv"
     if not f.exists():
         return None
     rows = list(csv.reader(f.open()))
@@ -332,7 +332,7 @@ def main():
                     "achieved": round(ach, 1), "peak": round(2 * bf16, 1), "unit": "TOP/s (int8 dense; TFLOP/s-equivalent)",
                     "frac": round(ach / (2 * bf16), 4), "peak_source": which, "peak_nominal": 4500.0,
                     "traffic": ncu_traffic_bytes("gemm_i8_tc_kernel<0, 2>") if be == 0 and S == 8192 and N == 14 else None,
-                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel, ncu --set full capture profiles/r01e_ncu_full_fast_summary.csv",
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel, ncu --set full capture profiles/r01f_ncu_full_fast_summary.csv",
                     "kernel_ms": round(t_gemm * 1e3, 4), "ops_per_launch": ops}
     elif ref is not None:
         tm = (ctypes.c_double * 4)()

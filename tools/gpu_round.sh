@@ -23,4 +23,7 @@ for mode in accu fast; do
 done
 ncu --set full --clock-control none --import-source on -k regex:"gemm_i8_tc|split_row|crt_kernel|stats_row" -s 5 -c 5 -f -o gpurun_out/${tag}_full_fast \
     python tools/profile_one.py 8192 14 fast 2 > gpurun_out/${tag}_ncu_full.log 2>&1
+# FP8 backend (config 5): the per-product GEMM, the combine pass and the FP8 split
+ncu --set full --clock-control none --import-source on -k regex:"gemm_i8_tc|f8_combine|split_row" -s 4 -c 4 -f -o gpurun_out/${tag}_full_fp8 \
+    python tools/profile_one.py 8192 14 fast 2 fp8 > gpurun_out/${tag}_ncu_full_fp8.log 2>&1
 ls -la gpurun_out | tail -12
