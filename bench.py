@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--backend", default="int8", choices=["int8", "fp8"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mg-variant", default="fused", choices=["int32", "residue", "fused"])
+    ap.add_argument("--k-local", type=int, default=0, help="K-slab per GPU in the K-sharded runs (default: --size, i.e. weak scaling in K; "
+                                                           "BASELINE.json config 3 = --size 16384 --k-local 2048 on 8 GPUs)")
     return ap.parse_args()
 
 
@@ -211,8 +213,8 @@ def main():
     fast = args.mode == "fast"
     be = 0 if args.backend == "int8" else 1
     m = n = S
-    k_local = S                      # every rank owns a k-slab of S columns/rows: weak scaling in K (total K = S * world)
-    k_total = S * (world if distributed else 1)
+    k_local = args.k_local or S      # every rank owns a k-slab: by default S columns/rows, i.e. weak scaling in K (total K = S * world)
+    k_total = k_local * (world if distributed else 1)
     dt = torch.float64
 
     # synthetic inputs, generated on the device with the reference harness' generator
@@ -300,8 +302,14 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_dev = timed(step_device, args.steps, warmup, sampler)
     clocks = sampler.stop() if rank == 0 else None
-    if mg is not None and os.environ.get("G8_MG_TRACE") == "1" and rank == 0:
-        print("[mg trace]", [(n_, round(t_, 3)) for n_, t_ in mg.trace_report()], file=sys.stderr)
+    if mg is not None and os.environ.get("G8_MG_TRACE") == "1":
+        mine = [(n_, round(t_, 3)) for n_, t_ in mg.trace_report()]
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+        if rank == 0:
+            print("[mg trace]", mine, file=sys.stderr)
+            for key in ("gemm+scatter", "barrier", "sum+crt", "split"):
+                print(f"[mg trace all ranks] {key}:", [dict(t).get(key) for t in allr], file=sys.stderr)
     ms_e2e = timed(step_e2e, max(2, min(args.steps, 5)), 1)
 
     flops = 2.0 * m * n * k_total

@@ -207,9 +207,12 @@ template <> struct EpiCfg<EPI_MOD_I8_SCATTER> { static constexpr int TILE_COL = 
 template <> struct EpiCfg<EPI_RAW_I32_SCATTER> { static constexpr int TILE_COL = 256, NACC = 1, NCHAIN = 1; };
 template <> struct EpiCfg<EPI_F8_BOUND_CPLX>  { static constexpr int TILE_COL = 128, NACC = 2, NCHAIN = 2; };
 template <> struct EpiCfg<EPI_F8_PROD>        { static constexpr int TILE_COL = 256, NACC = 1, NCHAIN = 1; };
-// EPI_MOD_I8_SCATTER staging: per epilogue warp 32 columns x (128 rows + 16 B pad); the pad makes the 16-byte shared stores of
-// the 32 lanes (one column each) bank-conflict free: 144 B stride = 36 banks -> lane l starts at bank 4l mod 32
-constexpr int SCAT_ROWS = 128, SCAT_PITCH = SCAT_ROWS + 16, SCAT_WARP_BYTES = 32 * SCAT_PITCH, SCAT_BYTES = 4 * SCAT_WARP_BYTES;
+// EPI_MOD_I8_SCATTER staging: per epilogue warp 32 columns x (SCAT_ROWS + 16 B pad); the pad makes the 16-byte shared stores of
+// the 32 lanes (one column each) bank-conflict free: a (16 mod 128)-byte stride puts lane l at bank 4l mod 32
+#ifndef G8_SCAT_ROWS
+#define G8_SCAT_ROWS 256 // rows per bulk copy: 256-byte segments measured 0-6 % faster than 128 over NVLink (costs one TMA stage: 5 instead of 6)
+#endif
+constexpr int SCAT_ROWS = G8_SCAT_ROWS, SCAT_PITCH = SCAT_ROWS + 16, SCAT_WARP_BYTES = 32 * SCAT_PITCH, SCAT_BYTES = 4 * SCAT_WARP_BYTES;
 template <int EPI> constexpr bool is_f8 = (EPI == EPI_F8_MOD || EPI == EPI_F8_BOUND || EPI == EPI_F8_RAW || EPI == EPI_F8_BOUND_CPLX || EPI == EPI_F8_PROD);
 
 // CG = 1: one CTA per tile (128 columns of C x TILE_COL rows).  CG = 2: a CTA pair (tcgen05 cta_group::2) shares a
@@ -221,11 +224,12 @@ template <int EPI, int CG = 1> struct KernelShape {
     static constexpr int STAGE_L    = TILE_LANE * BLOCK_K;         // bytes: lane-side operand (B_lo tile), per CTA
     static constexpr int STAGE_C    = TILE_COL / CG * BLOCK_K;     // bytes: column-side operand (A_lo tile), per CTA
     static constexpr int STAGE      = STAGE_L + STAGE_C;
-    static constexpr int NUM_STAGES = (220 * 1024) / STAGE > 8 ? 8 : (220 * 1024) / STAGE;
+    static constexpr int SCAT       = (EPI == EPI_MOD_I8_SCATTER || EPI == EPI_RAW_I32_SCATTER) ? SCAT_BYTES : 0; // epilogue staging
+    static constexpr int NUM_STAGES = (220 * 1024 - SCAT) / STAGE > 8 ? 8 : (220 * 1024 - SCAT) / STAGE;
     // TMEM is a ring of accumulator SLOTS of TILE_COL columns; a tile takes NACC consecutive slots.  With more slots than
     // NACC (2 vs 1, 4 vs 3) the MMAs of the next tile start while the epilogue still drains the previous one.
     static constexpr int NUM_BUF    = 512 / TILE_COL;
-    static constexpr int SMEM_BYTES = NUM_STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + ((EPI == EPI_MOD_I8_SCATTER || EPI == EPI_RAW_I32_SCATTER) ? SCAT_BYTES : 0);
+    static constexpr int SMEM_BYTES = NUM_STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + SCAT;
 };
 
 struct TileCoord {
@@ -482,8 +486,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                     }
                 }
             } else if constexpr (EPI == EPI_MOD_I8_SCATTER) {
-                // residues -> shared memory (this thread's column, 128 rows at a time) -> ONE 128-byte cp.async.bulk per thread into
-                // the owner's buffer: NVLink sees full 128-byte writes issued by the copy engine instead of 16-byte stores that
+                // residues -> shared memory (this thread's column, SCAT_ROWS rows at a time) -> ONE cp.async.bulk per thread into
+                // the owner's buffer: NVLink sees full 256-byte writes issued by the copy engine instead of 16-byte stores that
                 // stall the epilogue warps on remote latency.
                 const int32_t p = g8d_moduli[INT8][midx], pinv = g8d_pinv32[INT8][midx];
                 int8_t *dst = reinterpret_cast<int8_t *>(out_base) + (size_t)tc.unit * P.out_stride + (size_t)col_o * P.ldc + row0;
