@@ -68,15 +68,16 @@ struct PhaseTimer {
 };
 
 static bool device_ok() {
-    static int ok = -1;
-    if (ok < 0) {
-        int dev = 0, major = 0, minor = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    static int ok[64]; // per device: 0 unknown, 1 yes, 2 no
+    int dev = 0, major = 0, minor = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    int &v = ok[dev & 63];
+    if (!v) {
         cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
         cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
-        ok = (major == 10 && minor == 0) ? 1 : 0;
+        v = (major == 10 && minor == 0) ? 1 : 2;
     }
-    return ok == 1;
+    return v == 1;
 }
 
 static SplitArgs split_args(int is_A, int op, size_t rows, size_t k, const void *X, size_t ld, unsigned N, int16_t *sft,
@@ -98,6 +99,7 @@ static int gemm_impl(const g8_gemm_desc &d, double *phase_ns) {
     if (d.dtype < F32 || d.dtype > C64 || d.op_A < 0 || d.op_A > 2 || d.op_B < 0 || d.op_B > 2) return G8_STATUS_INVALID_VALUE;
     if (d.num_moduli < 2 || d.num_moduli > G8_MAX_MODULI) return G8_STATUS_INVALID_VALUE;
     if (d.backend != INT8 && d.backend != FP8) return G8_STATUS_INVALID_VALUE;
+    if (d.k > (size_t(1) << 17)) return G8_STATUS_INVALID_VALUE; // INT32 accumulation is exact only up to k = 2^17 (include/gemmul8.hpp:29)
     if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
     if (d.m == 0 || d.n == 0) return 0;
 

@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t 
     constexpr int VEC  = TR::cplx ? NV / 2 : NV; // rows per thread
     const size_t idx   = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const size_t col = idx / groups;
+    // (32-bit division whenever the index fits: the emulated 64-bit one costs ~60 instructions per thread)
+    const size_t col = (total <= 0xFFFFFFFFull) ? (size_t)((uint32_t)idx / (uint32_t)groups) : idx / groups;
     const size_t row = (idx - col * groups) * VEC;
     const int N      = c.num_moduli;
 
@@ -61,13 +62,14 @@ __global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t 
     const size_t pstride = c.plane_stride * (TR::cplx ? 2 : 1) * MIDB;
     const int tbl1 = N - 2, tbl2 = N - thresholds(BE).P_is_double - 1;
     constexpr double kOff = 4503599627370496.0 + (BE == INT8 ? 128.0 : 32768.0);
+    const int8_t *sp = src; // plane i: sp = src + i * pstride, advanced by addition (no 64-bit multiply per plane)
 #pragma unroll 4
-    for (int i = 0; i < N; ++i) {
+    for (int i = 0; i < N; ++i, sp += pstride) {
         double cd[NV];
         if constexpr (BE == INT8) {
             uint32_t w;
             if constexpr (PARTS == 0) {
-                w = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)i * pstride));
+                w = __ldg(reinterpret_cast<const uint32_t *>(sp));
             } else {
                 // K-sharded: add the per-shard residues byte-wise (dp4a against one-hot selectors sign-extends and adds in one
                 // instruction), reduce mod p_i again -- what g8_stage_residue_sum does, without the round trip through HBM
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t 
                 int x[PARTS > 0 ? PARTS : 1];
 #pragma unroll
                 for (int q = 0; q < PARTS; ++q)
-                    x[q] = (q < c.nparts) ? (int)__ldcs(reinterpret_cast<const uint32_t *>(src + (size_t)i * pstride + (size_t)q * c.part_stride)) : 0;
+                    x[q] = (q < c.nparts) ? (int)__ldcs(reinterpret_cast<const uint32_t *>(sp + (size_t)q * c.part_stride)) : 0;
 #pragma unroll
                 for (int q = 0; q < PARTS; ++q) {
                     a0 = __dp4a(x[q], 0x00000001, a0), a1 = __dp4a(x[q], 0x00000100, a1);
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t 
                 cd[j]            = __dadd_rn(__hiloint2double(0x43300000, (int)b), -kOff);
             }
         } else {
-            uint2 w = __ldg(reinterpret_cast<const uint2 *>(src + (size_t)i * pstride));
+            uint2 w = __ldg(reinterpret_cast<const uint2 *>(sp));
             w.x ^= 0x80008000u, w.y ^= 0x80008000u;
 #pragma unroll
             for (int j = 0; j < NV; ++j) {

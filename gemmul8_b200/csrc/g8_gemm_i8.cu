@@ -793,13 +793,12 @@ static bool make_plane_map(CUtensorMap *map, const void *base, size_t k_pad, siz
 }
 
 static int num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return n;
+    static int n[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int &v = n[dev & 63];
+    if (!v) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
 }
 
 // G8_GEMM_CTA_GROUP=1 forces the single-CTA kernel (debugging / A-B comparisons); default is the CTA-pair kernel
@@ -843,7 +842,11 @@ template <int EPI, int CG> static int launch_tc_cg(const GemmArgs &g, cudaStream
         P.tl_rot = (int)(((size_t)(g.rank + 1) % (size_t)g.world) * (g.owner_cols / (TILE_LANE * CG))) % P.tiles_l;
     }
 
-    static bool attr_set = false;
+    // per kernel instantiation AND per device (function attributes are per-device state; one process may drive several GPUs)
+    static bool attr_set_dev[64] = {};
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    bool &attr_set = attr_set_dev[cur_dev & 63];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_i8_tc_kernel<EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, KS::SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;

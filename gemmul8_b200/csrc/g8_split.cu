@@ -159,7 +159,10 @@ template <bool LARGE, int BE> __device__ __forceinline__ double level1(double x,
 template <int BE> __device__ __forceinline__ int32_t level2(double r, int idx) {
     const int32_t a1  = __double2loint(__dadd_rn(r, g8d_mbias[BE][idx]));
     const uint32_t q  = __umulhi((uint32_t)a1, g8d_mmagic[BE][idx]);
-    return (a1 - g8d_mhalf[BE][idx]) - (int32_t)(q * (uint32_t)g8d_moduli[BE][idx]);
+    // a1 - q * p first (one IMAD: q and a1 in registers, -p the single uniform operand), then - h: avoids re-materialising p in a register
+    uint32_t t;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(q), "r"(0u - (uint32_t)g8d_moduli[BE][idx]), "r"((uint32_t)a1));
+    return (int32_t)t - g8d_mhalf[BE][idx];
 }
 // x mod 1024, symmetric (FP8 modulus index 1; mod.hpp:79-93)
 __device__ __forceinline__ int32_t residue1024(double x) {
