@@ -287,3 +287,32 @@ def test_gemm_scatter_local_peers(env):
             torch.cuda.synchronize()
             for o in (0, 1):
                 assert torch.equal(bufs[o][:, :, :m], ref[:, o * nc:(o + 1) * nc, :m]), (epi, rank, o)
+
+
+@pytest.mark.parametrize("case", ["zgemm4096_int8_n18", "dgemm8192_fp8_n14"])
+def test_full_size_properties_other_configs(env, case):
+    """BASELINE.json configs 4 and 5 at their full sizes (the multi-product paths: per-product GEMM units in batches + combine pass):
+    run-to-run bit reproducibility, exact cancellation C - AB == 0 with alpha = -1, beta = 1, and a corner block against a wide matmul."""
+    torch, g8 = env.torch, __import__("gemmul8_b200")
+    if case.startswith("zgemm"):
+        S, N, dt, be, tol = 4096, 18, torch.complex128, 0, 1e-12
+    else:
+        S, N, dt, be, tol = 8192, 14, torch.float64, 1, 1e-9
+    A = g8.randmat(S, S, dt, seed=12345)
+    B = g8.randmat(S, S, dt, seed=54321)
+    C1 = torch.zeros(S * S, dtype=dt, device="cuda")
+    C2 = torch.zeros_like(C1)
+    tot, _, _ = g8.work_size(S, S, S, N, is_complex=dt.is_complex, backend=be)
+    work = torch.empty(tot, dtype=torch.uint8, device="cuda")
+    for fast in (False, True):
+        g8.gemm("N", "N", S, S, S, 1.0, A, S, B, S, 0.0, C1, S, N, fast, work, backend=be)
+        g8.gemm("N", "N", S, S, S, 1.0, A, S, B, S, 0.0, C2, S, N, fast, work, backend=be)
+        assert torch.equal(C1.view(torch.uint8), C2.view(torch.uint8))
+        g8.gemm("N", "N", S, S, S, -1.0, A, S, B, S, 1.0, C2, S, N, fast, work, backend=be)
+        assert float(C2.abs().max()) == 0.0
+        Am = A.view(S, S).t()[:192, :]
+        Bm = B.view(S, S).t()[:, :192]
+        ref = Am @ Bm
+        got = C1.view(S, S).t()[:192, :192]
+        rel = float((got - ref).abs().max() / ref.abs().max())
+        assert rel < tol * (50 if fast else 1), rel
