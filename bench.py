@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--backend", default="int8", choices=["int8", "fp8"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mg-variant", default="fused", choices=["int32", "residue", "fused"])
+    ap.add_argument("--mg-shard", default="k", choices=["k", "n"], help="multi-GPU sharding: k = K-sharded (the north-star path, default), "
+                                                                     "n = column-sharded (every rank holds A and a column slab of B / C; no bulk exchange)")
     ap.add_argument("--k-local", type=int, default=0, help="K-slab per GPU in the K-sharded runs (default: --size, i.e. weak scaling in K; "
                                                            "BASELINE.json config 3 = --size 16384 --k-local 2048 on 8 GPUs)")
     return ap.parse_args()
@@ -214,11 +216,15 @@ def main():
     be = 0 if args.backend == "int8" else 1
     m = n = S
     k_local = args.k_local or S      # every rank owns a k-slab: by default S columns/rows, i.e. weak scaling in K (total K = S * world)
-    k_total = k_local * (world if distributed else 1)
+    nshard = distributed and args.mg_shard == "n"
+    if nshard:
+        k_local = S                  # column-sharded: every rank has the full K and n_local = S columns (weak scaling in n)
+    k_total = k_local * (world if (distributed and not nshard) else 1)
+    n_total = n * (world if nshard else 1)
     dt = torch.float64
 
     # synthetic inputs, generated on the device with the reference harness' generator
-    A = g8.randmat(m, k_local, dt, phi=-1.0, seed=12345 + 1000 * rank, device=dev)
+    A = g8.randmat(m, k_local, dt, phi=-1.0, seed=12345 + (0 if (world > 1 and args.mg_shard == "n") else 1000 * rank), device=dev)
     B = g8.randmat(k_local, n, dt, phi=-1.0, seed=54321 + 1000 * rank, device=dev)
     C = torch.zeros(m * n, dtype=dt, device=dev)
 
@@ -240,7 +246,13 @@ def main():
     mg = None
     if distributed:
         from gemmul8_b200 import multi_gpu
-        mg = multi_gpu.KShardGemm(m, n, k_local, N, fastmode=fast, dtype=dt, device=dev, variant=args.mg_variant)
+        if nshard:
+            mg = multi_gpu.NShardGemm(m, n, k_local, N, fastmode=fast, dtype=dt, device=dev)
+            mg.local_out_elems = m * n
+            mg.local_out = lambda C_: C_
+            mg.trace_report = lambda: []
+        else:
+            mg = multi_gpu.KShardGemm(m, n, k_local, N, fastmode=fast, dtype=dt, device=dev, variant=args.mg_variant)
 
     def step_device():
         if ref is not None:
@@ -312,7 +324,7 @@ def main():
                 print(f"[mg trace all ranks] {key}:", [dict(t).get(key) for t in allr], file=sys.stderr)
     ms_e2e = timed(step_e2e, max(2, min(args.steps, 5)), 1)
 
-    flops = 2.0 * m * n * k_total
+    flops = 2.0 * m * n_total * k_total
     value = flops / (ms_dev * 1e-3) * 1e-12
     e2e_val = flops / (ms_e2e * 1e-3) * 1e-12
 
@@ -367,8 +379,9 @@ def main():
         "value": round(value, 2), "unit": "TFLOPS", "n_gpus": n_gpus, "steps": args.steps, "warmup": warmup,
         "ms_per_step": round(ms_dev, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int8 tensor-core residues (s8 x s8 -> s32) + f64 CRT; emulates f64", "data": "synthetic",
-        "config": {"workload": f"DGEMM {m}x{n}x{k_total} {args.backend.upper()} num_moduli={N} fastmode={int(fast)} opN/opN alpha=1 beta=0"
-                               + (f", K-sharded over {world} GPUs (k={k_local} per GPU), variant={args.mg_variant}" if distributed else ""),
+        "config": {"workload": f"DGEMM {m}x{n_total}x{k_total} {args.backend.upper()} num_moduli={N} fastmode={int(fast)} opN/opN alpha=1 beta=0"
+                               + (f", column-sharded over {world} GPUs (n={n} per GPU, A replicated, one all_reduce(MAX) in accurate mode)" if nshard else
+                                  (f", K-sharded over {world} GPUs (k={k_local} per GPU), variant={args.mg_variant}" if distributed else "")),
                    "inputs": "curand normal (phi=-1), seeds 12345/54321 as testing/make_matrix.hpp",
                    "l2": "inputs (2 x 512 MiB) and residue planes (2.6 GiB) are larger than the 126 MB L2; no explicit flush",
                    "timing": "CUDA events on the launch stream, max over ranks"},

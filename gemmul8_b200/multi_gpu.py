@@ -90,6 +90,11 @@ class CudaStages:
         api._check(self.lib.g8_stage_gemm_scatter(epi, A_lo.data_ptr(), strideA, B_lo.data_ptr(), strideB, m, n, k_pad, units, first, tbl, W,
                                                   peers.rank, out_stride, ldc, self._s()), "gemm_scatter")
 
+    def gemm_bound(self, A_lo, strideA, B_lo, strideB, m, n, k_pad, rowmax, colmax):
+        """bound GEMM of accurate mode with the row / column maxima fused into the epilogue (the bound product is never written)"""
+        api._check(self.lib.g8_stage_gemm(2, 0, A_lo.data_ptr(), strideA, B_lo.data_ptr(), strideB, m, n, k_pad, 1, 0, None, None, None, 0,
+                                          pad256(m), rowmax.data_ptr(), colmax.data_ptr(), self._s()), "gemm_bound")
+
     def maxabs_parts(self, parts, nparts, part_stride, rows, cols, ld, rowmax, colmax):
         api._check(self.lib.g8_stage_maxabs_i32_parts(parts.data_ptr(), nparts, part_stride, rows, cols, ld, rowmax.data_ptr(), colmax.data_ptr(),
                                                       self._s()), "maxabs_parts")
@@ -377,4 +382,51 @@ class KShardGemm:
         r0 = self.rank * nc
         st.crt(self.C_mid, mp, nc * mp, m, nc, C, m, self.sftA, self.sftB[r0:r0 + nc], alpha, beta)
         self._mark("crt")
+        return C
+
+
+class NShardGemm:
+    """Column-sharded multi-GPU emulated GEMM (SURVEY section 8e "N-shard"): rank r holds ALL of A (m x k) and the column slab
+    B[:, n_r] (k x n_local) and produces C[:, n_r].  No bulk exchange at all: the only cross-rank dependency is the accurate-mode
+    shift of A, which needs the row maxima of the bound product over ALL columns -> one all_reduce(MAX) of m int32 values.
+    Fast mode needs no communication.  Both modes are bit-identical to the single-GPU call on the full B (tests/test_gpu_multi.py)."""
+
+    def __init__(self, m, n_local, k, num_moduli, fastmode=False, dtype=torch.float64, device=None, stages=None, group=None):
+        if dtype not in (torch.float32, torch.float64):
+            raise NotImplementedError("N-sharded path: real S/D GEMM only")
+        self.group = group
+        self.m, self.n, self.k, self.N = m, n_local, k, num_moduli
+        self.fast, self.dtype = bool(fastmode), dtype
+        self.st = st = stages if stages is not None else CudaStages(dtype, num_moduli, device)
+        self.m_pad, self.k_pad, self.n_pad = pad256(m), pad256(k), pad256(n_local)
+        self.sizeA, self.sizeB = self.k_pad * self.m_pad, self.k_pad * n_local
+        N = num_moduli
+        self.A_lo = st.empty(self.sizeA * N, torch.int8)
+        self.B_lo = st.empty(self.sizeB * N, torch.int8)
+        self.sftA = st.zeros(self.m_pad, torch.int16)
+        self.sftB = st.zeros(self.n_pad, torch.int16)
+        self.C_mid = st.empty(N * n_local * self.m_pad, torch.int8)
+
+    def run(self, A, B, C, alpha=1.0, beta=0.0):
+        """A: flat m*k (ld = m), B: flat k*n_local (ld = k), C: flat m*n_local (ld = m); all column-major."""
+        st, m, n, k, N, mp = self.st, self.m, self.n, self.k, self.N, self.m_pad
+        amaxA, ssA = st.stats(True, 0, m, k, A, m)
+        amaxB, ssB = st.stats(False, 0, n, k, B, k)
+        if self.fast:
+            st.shift_from_stats(amaxA, ssA, 0, self.sftA)
+            st.shift_from_stats(amaxB, ssB, 0, self.sftB)
+        else:
+            st.shift_from_stats(amaxA, None, 1, self.sftA)
+            st.shift_from_stats(amaxB, None, 1, self.sftB)
+            st.split(True, 0, m, k, A, m, 3, self.sftA, self.A_lo, self.sizeA)     # bound planes (aliasing plane 0)
+            st.split(False, 0, n, k, B, k, 3, self.sftB, self.B_lo, self.sizeB)
+            rowmax, colmax = st.zeros(self.m_pad, torch.int32), st.zeros(self.n_pad, torch.int32)
+            st.gemm_bound(self.A_lo, self.sizeA, self.B_lo, self.sizeB, m, n, self.k_pad, rowmax, colmax)
+            dist.all_reduce(rowmax, op=dist.ReduceOp.MAX, group=self.group)          # the ONLY collective of this mode
+            st.finalize_shift(self.sftA, rowmax, m)
+            st.finalize_shift(self.sftB, colmax, n)
+        st.split(True, 0, m, k, A, m, 0, self.sftA, self.A_lo, self.sizeA)
+        st.split(False, 0, n, k, B, k, 0, self.sftB, self.B_lo, self.sizeB)
+        st.gemm(0, self.A_lo, self.sizeA, self.B_lo, self.sizeB, m, n, self.k_pad, N, self.C_mid, n * mp, mp)
+        st.crt(self.C_mid, mp, n * mp, m, n, C, m, self.sftA, self.sftB, alpha, beta)
         return C

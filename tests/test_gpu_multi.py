@@ -67,6 +67,66 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _nshard_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import gemmul8_b200 as g8
+        from gemmul8_b200 import multi_gpu
+
+        ok_all = True
+        for dtype, N in ((torch.float64, 14), (torch.float32, 6)):
+            m, nl, k = 300, 160, 700
+            n = nl * world
+            A = g8.randmat(m, k, dtype, phi=1.0, seed=31, device=f"cuda:{rank}")
+            B = g8.randmat(k, n, dtype, phi=1.0, seed=32, device=f"cuda:{rank}")
+            Br = B.view(n, k)[rank * nl:(rank + 1) * nl].contiguous().view(-1)     # columns n_r of B
+            for fast in (False, True):
+                Cfull = torch.zeros(m * n, dtype=dtype, device=f"cuda:{rank}")
+                tot, _, _ = g8.work_size(m, n, k, N)
+                work = torch.empty(tot, dtype=torch.uint8, device=f"cuda:{rank}")
+                g8.gemm("N", "N", m, n, k, 1.0, A, m, B, k, 0.0, Cfull, m, N, fast, work)
+                plan = multi_gpu.NShardGemm(m, nl, k, N, fastmode=fast, dtype=dtype, device=f"cuda:{rank}")
+                C = torch.zeros(m * nl, dtype=dtype, device=f"cuda:{rank}")
+                plan.run(A, Br, C)
+                torch.cuda.synchronize()
+                want = Cfull.view(n, m)[rank * nl:(rank + 1) * nl].reshape(-1)
+                ok = torch.equal(C, want)            # BOTH modes: bit-identical to the single-GPU call on the full B
+                ok_all &= ok
+                if not ok:
+                    print(f"rank {rank} N-shard mismatch dtype={dtype} fast={fast}", flush=True)
+        q.put((rank, ok_all))
+    except Exception:
+        q.put((rank, False))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nshard_nccl_matches_single_gpu(cuda):
+    import torch
+    import torch.multiprocessing as mp
+
+    world = min(torch.cuda.device_count(), 2)
+    if world < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nshard_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+    assert all(ok for _, ok in res), res
+
+
 def test_kshard_nccl_matches_single_gpu(cuda):
     import torch
     import torch.multiprocessing as mp
