@@ -349,7 +349,8 @@ def main():
         t_gemm = phases[1] * 1e-9
         ach = ops / t_gemm * 1e-12
         roofline = {"bound": "tensor", "kernel": "gemm_i8_tc_kernel<EPI_MOD_I8> (tcgen05.mma kind::i8, all moduli in one launch)",
-                    "achieved": round(ach, 1), "peak": round(2 * bf16, 1), "unit": "TOP/s (int8 dense; TFLOP/s-equivalent)",
+                    "achieved": round(ach, 1), "peak": round(2 * bf16, 1), "unit": "TFLOP/s",
+                    "unit_note": "dense int8 (or fp8) tensor operations per second, counted like FLOPs (2 per multiply-add)",
                     "frac": round(ach / (2 * bf16), 4), "peak_source": which, "peak_nominal": 4500.0,
                     "traffic": ncu_traffic_bytes("gemm_i8_tc_kernel<0, 2>") if be == 0 and S == 8192 and N == 14 else None,
                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel, ncu --set full capture profiles/r01f_ncu_full_fast_summary.csv",

@@ -8,7 +8,8 @@
 //    no cuBLAS / cuBLASLt routine runs on the hot path;
 //  * the call is asynchronous; the returned vector {split, gemm, requant, crt} [ns] is all zeros unless the
 //    environment variable GEMMUL8_PHASE_TIMING=1 is set (then the call synchronises, as the reference always does);
-//  * Backend::FP8 is not implemented in this build: gemmLt<T, Backend::FP8> reports an error on stderr and leaves C untouched.
+//  * Backend::FP8 (gemmLt only, like the reference) runs the e4m3 emulation on tcgen05 kind::f8f6f4 for all four types; its
+//    accurate-mode shifts may differ by one from the reference's on a floor() boundary (f32 bound product).
 #pragma once
 #include <cublasLt.h>
 #include <cublas_v2.h>

@@ -33,7 +33,7 @@ enum { G8_OP_N = 0, G8_OP_T = 1, G8_OP_C = 2 };
 enum {
     G8_STATUS_SUCCESS        = 0,
     G8_STATUS_INVALID_VALUE  = 10001, /* bad enum / null pointer / num_moduli out of [2,20] (FP64) or [2,13] (FP32) / k > 2^17 */
-    G8_STATUS_NOT_SUPPORTED  = 10002, /* backend or shape this build does not implement (e.g. FP8 backend) */
+    G8_STATUS_NOT_SUPPORTED  = 10002, /* workspace too small for the scratch a path needs (cannot happen with a g8_work_size()-sized buffer) */
     G8_STATUS_NO_DEVICE_CODE = 10003  /* the sm_100a kernels cannot run on this device: there is NO fallback path */
 };
 
@@ -84,7 +84,8 @@ int g8_stage_split(int dtype, int is_A, int op, size_t rows, size_t k, const voi
 int g8_stage_finalize_shift(int16_t *sft, const int32_t *cmax, size_t count, unsigned num_moduli, void *stream);
 
 /* Stage 2: the low-precision GEMMs over planes (src/matmult.hpp:120-302 + src/conv_hi2mid_*.hpp).
- * epilogue: 0 mod-p int8, 1 raw int32, 2 row/col max (bound GEMM), 3 complex mod-p, 4 complex bound max.
+ * epilogue (GemmEpilogue in csrc/g8_internal.cuh): 0 mod-p int8, 1 raw int32, 2 row/col max (bound GEMM), 3 complex mod-p (fused 3M tile),
+ * 4 complex bound max, 5 FP8 three-piece tile, 6 FP8 bound max, 7 FP8 raw f32 (tests).
  * use_simt != 0 selects the slow dp4a cross-check kernel (tests only). */
 int g8_stage_gemm(int epilogue, int use_simt, const int8_t *A_lo, size_t strideA, const int8_t *B_lo, size_t strideB, size_t m,
                   size_t n, size_t k_pad, int num_units, int first_modulus, const int *groupA, const int *groupB, void *out,
