@@ -13,9 +13,12 @@
 // walks rows r of C, so that after tcgen05.ld.32x32b every thread holds a run of CONSECUTIVE ROWS of one
 // column of the column-major output and can store 16 bytes at a time.
 //
-// One persistent CTA per SM; work = (unit, tile) pairs in unit-major order so that all SMs work on the
-// same modulus (its two operand planes stay L2-resident); the TMEM accumulator is double-buffered so the
-// epilogue of tile t overlaps the MMAs of tile t+1.
+// One persistent CTA per SM, by default grouped into CTA pairs (cta_group::2, one 256 x 256 tile per pair); work = (unit, tile)
+// pairs in unit-major order so that all SMs work on the same plane pair (it stays L2-resident); the TMEM accumulator is a ring
+// of slots so the epilogue of tile t overlaps the MMAs of tile t+1.  A "unit" is ONE low-precision product: a modulus (real INT8),
+// one of the three 3M products of a modulus (complex INT8) or one FP8 piece product (kind::f8f6f4); multi-product residues are
+// recombined by a small pass in g8_api.cu.  The *_SCATTER epilogues are the fused GEMM -> NVLink exchange of the K-sharded
+// multi-GPU path (residue tiles leave through shared memory + cp.async.bulk into the owning rank's peer-mapped buffer).
 #include "g8_internal.cuh"
 
 #include <cuda.h> // CUtensorMap (types only; the encoder is fetched through the runtime, no -lcuda)
