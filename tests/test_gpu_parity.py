@@ -316,3 +316,45 @@ def test_full_size_properties_other_configs(env, case):
         got = C1.view(S, S).t()[:192, :192]
         rel = float((got - ref).abs().max() / ref.abs().max())
         assert rel < tol * (50 if fast else 1), rel
+
+
+@pytest.mark.parametrize("dtype,N,fast,be", [(np.float64, 14, False, 0), (np.float32, 6, True, 0), (np.complex128, 8, False, 0), (np.float64, 9, False, 1)])
+def test_cuda_graph_capture_and_replay(env, dtype, N, fast, be):
+    """g8_gemm never synchronises (no host round trip between the stages), so a whole emulated GEMM can be captured into a CUDA
+    graph and replayed -- the way to amortise the launch cost of small problems.  Replays on NEW input data must equal eager calls
+    bit for bit (tensor maps, scalars and workspace pointers are baked into the graph; the data is not)."""
+    torch, H = env.torch, env.H
+    import gemmul8_b200 as g8
+
+    rng = np.random.default_rng(23)
+    m, n, k = 256, 192, 384
+    tdt = H.NP2T[np.dtype(dtype)]
+    cplx = np.dtype(dtype).kind == "c"
+    dA = torch.zeros(m * k, dtype=tdt, device="cuda")
+    dB = torch.zeros(k * n, dtype=tdt, device="cuda")
+    dC = torch.zeros(m * n, dtype=tdt, device="cuda")
+    tot, _, _ = g8.work_size(m, n, k, N, is_complex=cplx, backend=be)
+    work = torch.zeros(tot, dtype=torch.uint8, device="cuda")
+
+    def load(seed):
+        r = np.random.default_rng(seed)
+        A = H.rand_matrix(r, (m, k), dtype); B = H.rand_matrix(r, (k, n), dtype)
+        dA.copy_(H.to_dev_colmajor(A)[0]); dB.copy_(H.to_dev_colmajor(B)[0])
+        return A, B
+
+    load(1)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):       # warm-up outside capture (function attributes, lazy module loading)
+        g8.gemm("N", "N", m, n, k, 1.0, dA, m, dB, k, 0.0, dC, m, N, fast, work, backend=be)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g8.gemm("N", "N", m, n, k, 1.0, dA, m, dB, k, 0.0, dC, m, N, fast, work, backend=be)
+    for seed in (2, 3):
+        A, B = load(seed)
+        dC.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        got = H.from_dev_colmajor(dC, m, n, m)
+        want = H.run_gemm(A, B, "N", "N", N, fast, backend=be)
+        assert H.bits_equal(got, want), H.first_diff(got, want, f"graph replay seed {seed}")
