@@ -241,8 +241,7 @@ struct TileCoord {
 
 // unit-major; inside a unit, bands of GROUP lane-tiles are swept along the column-tile direction so that
 // the CTAs running concurrently share a small set of operand panels in L2.
-__device__ __forceinline__ TileCoord tile_coord(int t, int tiles_l, int tiles_c, int tl_rot = 0) {
-    constexpr int GROUP = 16;
+__device__ __forceinline__ TileCoord tile_coord(int t, int tiles_l, int tiles_c, int tl_rot = 0, int GROUP = 16) {
     const int per_unit  = tiles_l * tiles_c;
     TileCoord r;
     r.unit        = t / per_unit;
@@ -271,6 +270,7 @@ struct KParams {
     void *peer_out[G8_MAX_PEERS];
     int owner_cols;
     int prods, set_stride; // EPI_F8_PROD
+    int group;  // lane tiles per rasterisation band (tile_coord)
     int tl_rot; // rotation of the lane-tile sweep so that the ranks do not all target the same owner at the same time
 };
 
@@ -346,7 +346,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             for (int t = cid; t < total_tiles; t += ncl) {
-                const TileCoord tc = tile_coord(t, P.tiles_l, P.tiles_c, P.tl_rot);
+                const TileCoord tc = tile_coord(t, P.tiles_l, P.tiles_c, P.tl_rot, P.group);
                 for (int acc = 0; acc < EC::NACC; ++acc)
                     for (int c = 0; c < EC::NCHAIN; ++c) {
                         int planeA, planeB;
@@ -441,7 +441,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
         int buf = 0;
         uint32_t tphase = 0;
         for (int t = cid; t < total_tiles; t += ncl) {
-            const TileCoord tc = tile_coord(t, P.tiles_l, P.tiles_c, P.tl_rot);
+            const TileCoord tc = tile_coord(t, P.tiles_l, P.tiles_c, P.tl_rot, P.group);
             // the NACC accumulators of this tile sit in consecutive ring slots
             uint32_t ta[3] = {0, 0, 0};
             int sb = buf;
@@ -836,6 +836,8 @@ template <int EPI, int CG> static int launch_tc_cg(const GemmArgs &g, cudaStream
     P.rowmax = g.rowmax, P.colmax = g.colmax;
     P.inflate = (float)(g.k_true + 1) * 0x1p-24f;
     P.owner_cols = 0, P.tl_rot = 0;
+    static const int group_pref = [] { const char *e = getenv("G8_GEMM_GROUP"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 16; }();
+    P.group = group_pref;
     P.prods = g.prods > 0 ? g.prods : (EPI == EPI_F8_PROD ? 3 : 1), P.set_stride = g.set_stride;
     if (g.owner_cols) {
         // the scatter is tile-granular: every lane tile (TILE_LANE * CG columns) must fall inside one owner's slab
