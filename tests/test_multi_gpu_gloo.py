@@ -205,7 +205,7 @@ def _worker(rank, world, port, variant, fast, dtype_name, q):
         t_dt = {"float64": torch.float64, "float32": torch.float32}[dtype_name]
         N = 14 if dtype_name == "float64" else 6
         rng = np.random.default_rng(42)  # same stream on both ranks
-        m, n, kl = 37, 26, 40
+        m, n, kl = (37, 26, 40) if world == 2 else (21, 4 * world, 24)
         A = ((rng.random((m, kl * world)) - 0.5) * np.exp(rng.standard_normal((m, kl * world)))).astype(np_dt)
         B = ((rng.random((kl * world, n)) - 0.5) * np.exp(rng.standard_normal((kl * world, n)))).astype(np_dt)
         Ar, Br = A[:, rank * kl:(rank + 1) * kl], B[rank * kl:(rank + 1) * kl, :]
@@ -301,3 +301,19 @@ def test_nshard_two_ranks_matches_single_process(fast):
     for rank, ok, ok_shift in res:
         assert ok_shift, f"rank {rank}: shifts differ from the single-process oracle"
         assert ok, f"rank {rank}: C slab differs from the single-process oracle"
+
+
+def test_kshard_fused_eight_ranks():
+    """world_size 8 (the box size): the fused variant takes its > 4-shard branch (separate residue-sum pass before the CRT)"""
+    world, port = 8, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, "fused", False, "float64", q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, ok_shift in res:
+        assert ok_shift and ok, f"rank {rank}: differs from the single-process oracle"
