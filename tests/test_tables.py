@@ -6,6 +6,7 @@ import sys
 from math import gcd
 from pathlib import Path
 
+import numpy as np
 import pytest
 
 from gemmul8_b200 import tables as T
@@ -63,3 +64,81 @@ def test_generated_header_is_current():
     pytest.importorskip("mpmath")
     r = subprocess.run([sys.executable, str(ROOT / "tools/gen_tables.py"), "--check"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("be", ["INT8", "FP8"])
+def test_level2_residue_formula_exhaustive(be):
+    """Our split's level-2 step (DESIGN 3.1, g8_split.cu:level2): for a level-1 remainder r with |r| <= 0.52 M_g,
+    a1 = r + h + K p >= 0, q = umulhi(a1, ceil(2^32/p)), s = (a1 - h) - q p must be THE symmetric residue of r mod p.
+    Checked by brute force over the whole admissible range of every modulus (no sampling)."""
+    F = T.fast_mod_tables(be)
+    mods = T.moduli(be)
+    for gi, members in enumerate(F["groups"]):
+        M = F["grpM"][gi]
+        vmax = int(0.52 * M) + 2
+        r = np.arange(-vmax, vmax + 1, dtype=np.int64)
+        for i in members:
+            p, h, mg = mods[i], F["half"][i], F["magic"][i]
+            ibias = int(F["bias"][i] - T.MAGIC_RINT)          # h + K p, the integer part of the DADD bias
+            a1 = r + ibias
+            assert a1.min() >= 0 and a1.max() < 2 ** 31
+            q = (a1 * mg) >> 32                                # umulhi on 32-bit operands
+            s = (a1 - h) - q * p
+            assert np.array_equal(q, a1 // p), (be, p)
+            want = ((r + h) % p) - h                           # symmetric representative in [-h, p - 1 - h]
+            assert np.array_equal(s, want), (be, p)
+            assert s.min() >= -h and s.max() <= p - 1 - h
+
+
+@pytest.mark.parametrize("be", ["INT8", "FP8"])
+def test_level1_group_remainder_bound(be):
+    """level 1: r = x - M rint(x / M) evaluated in binary64 with the 1.5 * 2^52 trick stays an exact integer with |r| <= 0.52 M
+    for |x| < 2^63 -- sampled at the extremes (largest x, values next to the rounding boundaries of x / M)."""
+    F = T.fast_mod_tables(be)
+    rng = np.random.default_rng(0)
+    for M in F["grpM"]:
+        xs = np.concatenate([rng.integers(-2 ** 62, 2 ** 62, size=20000) * 2 + 1, [2 ** 63 - 2 ** 10, -(2 ** 63 - 2 ** 10)],
+                             (np.arange(1, 2000) * M + M // 2).astype(np.int64), (np.arange(1, 2000) * M + M // 2 + 1).astype(np.int64)])
+        x = xs.astype(np.float64)                              # the split holds trunc(a 2^s) as a double (<= 53 significant bits)
+        xi = x.astype(object)                                  # exact integer values of those doubles
+        q = (x * (1.0 / M) + T.MAGIC_RINT) - T.MAGIC_RINT
+        r = np.array([float(v) for v in (np.array([int(a) for a in x], dtype=object) - np.array([int(b) for b in q], dtype=object) * M)])
+        assert np.all(np.abs(r) <= 0.52 * M + 2), (be, M, np.abs(r).max() / M)
+
+
+def test_fp8_piece_decomposition_exhaustive():
+    """FP8 backend split (g8_split.cu:split_store_f8): every symmetric residue r of every FP8 modulus is written as small integers
+    that e4m3 represents exactly (|piece| <= 16): square moduli r = sqrt(p) hi + lo with hi = rint(r / sqrt(p)); the others
+    r = 16 hi + lo with hi = sign(r) ceil(|r| / 16), plus the Karatsuba piece hi + lo (mod.hpp:159-189).  The device evaluates this
+    with binary32 magic-constant arithmetic (no conversion instructions); the same arithmetic is replayed here with numpy float32
+    for ALL residues and checked against the integer definitions."""
+    f32 = np.float32
+    magic = f32(12582912.0)
+    mods = T.moduli("FP8")
+    for idx, p in enumerate(mods):
+        h = p // 2
+        r = np.arange(-h, h + 1, dtype=np.int64)
+        af = (np.int32(0x4B400000) + r.astype(np.int32)).view(np.float32) - magic      # int -> float without I2F
+        assert np.array_equal(af.astype(np.int64), r)
+        if idx < 6:
+            sq = f32(T.FP8_SQRT_MODULI[idx])
+            assert int(sq) ** 2 == p
+            inv = f32(1.0) / sq
+            hf = ((af * inv) + magic) - magic
+            lf = af - sq * hf                                                             # exact: small integers
+            want_h = np.rint((r.astype(np.float32) * inv)).astype(np.int64)
+            assert np.array_equal(hf.astype(np.int64), want_h)
+            assert np.array_equal((int(sq) * hf.astype(np.int64) + lf.astype(np.int64)), r)
+            pieces = [hf, lf]
+        else:
+            y = np.abs(af) * f32(0.0625) + f32(0.9375 - 0.46875)
+            hm = (y + magic) - magic
+            hf = np.copysign(hm, af)
+            lf = af - f32(16.0) * hf
+            want_h = np.sign(r) * -(-np.abs(r) // 16)                                    # sign(r) * ceil(|r| / 16)
+            assert np.array_equal(hf.astype(np.int64), want_h), p
+            assert np.array_equal(16 * hf.astype(np.int64) + lf.astype(np.int64), r)
+            pieces = [hf, lf, hf + lf]
+        for pc in pieces:
+            v = pc.astype(np.int64)
+            assert np.array_equal(v.astype(np.float32), pc) and np.abs(v).max() <= 16, (p, np.abs(v).max())
