@@ -11,6 +11,7 @@
 #include "../../include/gemmul8_c.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 
@@ -63,19 +64,25 @@ struct PhaseTimer {
         cudaEventElapsedTime(&ms, ev[1], ev[2]); ns[1] = ms * 1e6;
         ns[2] = 0.0; // requantisation is fused into the GEMM epilogue
         cudaEventElapsedTime(&ms, ev[2], ev[4]); ns[3] = ms * 1e6;
-        for (auto &e : ev) cudaEventDestroy(e);
     }
+    ~PhaseTimer() { // also on the early error returns of gemm_impl
+        if (on)
+            for (auto &e : ev) cudaEventDestroy(e);
+    }
+    PhaseTimer(const PhaseTimer &) = delete;
+    PhaseTimer &operator=(const PhaseTimer &) = delete;
 };
 
 static bool device_ok() {
-    static int ok[64]; // per device: 0 unknown, 1 yes, 2 no
+    static std::atomic<int> ok[64]; // per device: 0 unknown, 1 yes, 2 no (racing first calls compute the same value)
     int dev = 0, major = 0, minor = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return false;
-    int &v = ok[dev & 63];
+    int v = ok[dev & 63].load(std::memory_order_relaxed);
     if (!v) {
         cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
         cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
         v = (major == 10 && minor == 0) ? 1 : 2;
+        ok[dev & 63].store(v, std::memory_order_relaxed);
     }
     return v == 1;
 }
@@ -100,6 +107,9 @@ static int gemm_impl(const g8_gemm_desc &d, double *phase_ns) {
     if (d.num_moduli < 2 || d.num_moduli > G8_MAX_MODULI) return G8_STATUS_INVALID_VALUE;
     if (d.backend != INT8 && d.backend != FP8) return G8_STATUS_INVALID_VALUE;
     if (d.k > (size_t(1) << 17)) return G8_STATUS_INVALID_VALUE; // INT32 accumulation is exact only up to k = 2^17 (include/gemmul8.hpp:29)
+    // FP8: the piece products reach 16 * 16 = 256 and are summed in binary32: exact only while 256 k <= 2^24 (SURVEY appendix B;
+    // the reference documents 2^17 for both backends and silently loses exactness beyond 2^16 -- we refuse instead)
+    if (d.backend == FP8 && d.k > (size_t(1) << 16)) return G8_STATUS_INVALID_VALUE;
     if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
     if (d.m == 0 || d.n == 0) return 0;
 
@@ -468,6 +478,7 @@ __attribute__((visibility("default"))) int g8_stage_crt(int dtype, const void *C
                  size_t ldc, const int16_t *sftA, const int16_t *sftB, const void *alpha, const void *beta, void *stream) {
     if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
     if (!C_mid || !C || !sftA || !sftB || !alpha || !beta || num_moduli < 2 || num_moduli > G8_MAX_MODULI) return G8_STATUS_INVALID_VALUE;
+    if (ldmid % 8 || plane_stride % 8 || reinterpret_cast<uintptr_t>(C_mid) % 8) return G8_STATUS_INVALID_VALUE; // 64-bit residue loads
     CrtArgs c{};
     c.C_mid = C_mid, c.ldmid = ldmid, c.plane_stride = plane_stride, c.m = m, c.n = n, c.num_moduli = (int)num_moduli;
     c.C = C, c.ldc = ldc, c.sftA = sftA, c.sftB = sftB, c.alpha = alpha, c.beta = beta;
@@ -479,7 +490,8 @@ __attribute__((visibility("default"))) int g8_stage_crt_parts(int dtype, const v
                                                                const void *beta, void *stream) {
     if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
     if (!parts || !C || !sftA || !sftB || !alpha || !beta || num_moduli < 2 || num_moduli > G8_MAX_MODULI) return G8_STATUS_INVALID_VALUE;
-    if (nparts < 1 || nparts > G8_MAX_PEERS || part_stride % 4 || (dtype != F32 && dtype != F64)) return G8_STATUS_INVALID_VALUE;
+    if (nparts < 1 || nparts > G8_MAX_PEERS || part_stride % 8 || (dtype != F32 && dtype != F64)) return G8_STATUS_INVALID_VALUE;
+    if (ldmid % 8 || plane_stride % 8 || reinterpret_cast<uintptr_t>(parts) % 8) return G8_STATUS_INVALID_VALUE; // 64-bit residue loads
     CrtArgs c{};
     c.C_mid = parts, c.ldmid = ldmid, c.plane_stride = plane_stride, c.m = m, c.n = n, c.num_moduli = (int)num_moduli;
     c.C = C, c.ldc = ldc, c.sftA = sftA, c.sftB = sftB, c.alpha = alpha, c.beta = beta;

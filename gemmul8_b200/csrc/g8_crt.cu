@@ -8,8 +8,9 @@
 //                                                 q = rint(invP*H); r = fma(P.y, q, fma(P.x, q, H) + L)
 //   AB = scalbn((T)r, sftA[row] + sftB[col]);  then C = AB | C+AB | -AB | C-AB | fma(beta, C, alpha*AB).
 // What changes is the memory access and the instruction mix: each thread owns 8 consecutive residues of one column
-// (one 64-bit load per plane, 128-bit stores), and int8 -> double goes through a mantissa splice + one DADD
-// instead of I2F.F64 (quarter-rate pipe), instead of one element per thread with N strided byte loads.
+// (one 64-bit load per plane, 128-bit stores; the per-plane address / constant / loop overhead is shared by 8 results),
+// and int8 -> double goes through a mantissa splice + one DADD instead of I2F.F64 (quarter-rate pipe), instead of one
+// element per thread with N strided byte loads.
 #include "g8_internal.cuh"
 
 namespace g8 {
@@ -30,12 +31,19 @@ __device__ __forceinline__ float  scal(float v, int s) { return scalbnf(v, s); }
 __device__ __forceinline__ float  fma_(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
 
+// int8 / int16 residue (already XORed with the sign bit) -> double without a conversion instruction and without re-materialising the
+// constant high word: `tmpl` is a register pair whose high word stays 0x43300000 (2^52); PRMT rewrites only its low word with the
+// selected byte(s), and ONE DADD removes 2^52 + bias.  (Written as asm because the compiler otherwise emits PRMT + MOV per value.)
+template <int SEL> __device__ __forceinline__ double splice_low(double &tmpl, uint32_t w, double off) {
+    asm("{\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %0;\n\tprmt.b32 lo, %1, 0, %2;\n\tmov.b64 %0, {lo, hi};\n\t}" : "+d"(tmpl) : "r"(w), "n"(SEL));
+    return __dadd_rn(tmpl, off);
+}
+
 struct Scalars {
     double ar, ai, br, bi; // host scalars widened (exact); used in MODE 4
 };
 
-constexpr int CRT_NV = 4; // residue bytes (= scalar outputs) per thread: one 32-bit load per plane (128 B per warp);
-                          // small per-thread state -> full occupancy hides the serial FMA chains
+constexpr int CRT_NV = 8; // residue bytes (= scalar outputs) per thread: one 64-bit load per plane (256 B per warp)
 
 // MODE: 0 C=AB, 1 C+=AB, 2 C=-AB, 3 C-=AB, 4 general (host scalars), 5 general (device scalars)
 // PARTS: 0 = plain C_mid; 2 / 4 / 8 = K-sharded, up to that many per-shard residue arrays (c.nparts of them are real)
@@ -62,47 +70,53 @@ __global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t 
     const size_t pstride = c.plane_stride * (TR::cplx ? 2 : 1) * MIDB;
     const int tbl1 = N - 2, tbl2 = N - thresholds(BE).P_is_double - 1;
     constexpr double kOff = 4503599627370496.0 + (BE == INT8 ? 128.0 : 32768.0);
+    // (the high word is made opaque to the compiler -- total >> 63 is 0 -- so that it is kept in the register pair instead of being
+    //  re-materialised with a MOV in front of every conversion)
+    const int hi52 = 0x43300000 | (int)(total >> 63);
+    double tmplA = __hiloint2double(hi52, 0), tmplB = __hiloint2double(hi52, 1); // see splice_low
     const int8_t *sp = src; // plane i: sp = src + i * pstride, advanced by addition (no 64-bit multiply per plane)
 #pragma unroll 4
     for (int i = 0; i < N; ++i, sp += pstride) {
         double cd[NV];
         if constexpr (BE == INT8) {
-            uint32_t w;
+            uint32_t w[NV / 4];
             if constexpr (PARTS == 0) {
-                w = __ldg(reinterpret_cast<const uint32_t *>(sp));
+                const uint2 v = __ldg(reinterpret_cast<const uint2 *>(sp));
+                w[0] = v.x, w[1] = v.y;
             } else {
                 // K-sharded: add the per-shard residues byte-wise (dp4a against one-hot selectors sign-extends and adds in one
-                // instruction), reduce mod p_i again -- what g8_stage_residue_sum does, without the round trip through HBM
-                int32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                // constant trip count (PARTS, predicated) so that the loads of all shards -- and of the unrolled moduli --
-                // are in flight together
-                int x[PARTS > 0 ? PARTS : 1];
+                // instruction), reduce mod p_i again -- what g8_stage_residue_sum does, without the round trip through HBM.
+                // Constant trip count (PARTS, predicated) so that the loads of all shards are in flight together.
+                uint2 x[PARTS > 0 ? PARTS : 1];
 #pragma unroll
                 for (int q = 0; q < PARTS; ++q)
-                    x[q] = (q < c.nparts) ? (int)__ldcs(reinterpret_cast<const uint32_t *>(sp + (size_t)q * c.part_stride)) : 0;
-#pragma unroll
-                for (int q = 0; q < PARTS; ++q) {
-                    a0 = __dp4a(x[q], 0x00000001, a0), a1 = __dp4a(x[q], 0x00000100, a1);
-                    a2 = __dp4a(x[q], 0x00010000, a2), a3 = __dp4a(x[q], 0x01000000, a3);
-                }
+                    x[q] = (q < c.nparts) ? __ldcs(reinterpret_cast<const uint2 *>(sp + (size_t)q * c.part_stride)) : make_uint2(0u, 0u);
                 const int32_t p = g8d_moduli[INT8][i], pinv = g8d_pinv32[INT8][i];
-                a0 = mod_i32(a0, p, pinv), a1 = mod_i32(a1, p, pinv), a2 = mod_i32(a2, p, pinv), a3 = mod_i32(a3, p, pinv);
-                w = (uint32_t)(a0 & 0xFF) | ((uint32_t)(a1 & 0xFF) << 8) | ((uint32_t)(a2 & 0xFF) << 16) | ((uint32_t)a3 << 24);
-            }
-            w ^= 0x80808080u;
 #pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                const uint32_t b = __byte_perm(w, 0u, 0x4440 + j);
-                cd[j]            = __dadd_rn(__hiloint2double(0x43300000, (int)b), -kOff);
+                for (int h = 0; h < 2; ++h) {
+                    int32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+                    for (int q = 0; q < PARTS; ++q) {
+                        const int xv = (int)(h ? x[q].y : x[q].x);
+                        a0 = __dp4a(xv, 0x00000001, a0), a1 = __dp4a(xv, 0x00000100, a1);
+                        a2 = __dp4a(xv, 0x00010000, a2), a3 = __dp4a(xv, 0x01000000, a3);
+                    }
+                    a0 = mod_i32(a0, p, pinv), a1 = mod_i32(a1, p, pinv), a2 = mod_i32(a2, p, pinv), a3 = mod_i32(a3, p, pinv);
+                    w[h] = (uint32_t)(a0 & 0xFF) | ((uint32_t)(a1 & 0xFF) << 8) | ((uint32_t)(a2 & 0xFF) << 16) | ((uint32_t)a3 << 24);
+                }
             }
+            w[0] ^= 0x80808080u, w[1] ^= 0x80808080u;
+            cd[0] = splice_low<0x4440>(tmplA, w[0], -kOff), cd[1] = splice_low<0x4441>(tmplB, w[0], -kOff);
+            cd[2] = splice_low<0x4442>(tmplA, w[0], -kOff), cd[3] = splice_low<0x4443>(tmplB, w[0], -kOff);
+            cd[4] = splice_low<0x4440>(tmplA, w[1], -kOff), cd[5] = splice_low<0x4441>(tmplB, w[1], -kOff);
+            cd[6] = splice_low<0x4442>(tmplA, w[1], -kOff), cd[7] = splice_low<0x4443>(tmplB, w[1], -kOff);
         } else {
-            uint2 w = __ldg(reinterpret_cast<const uint2 *>(sp));
-            w.x ^= 0x80008000u, w.y ^= 0x80008000u;
-#pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                const uint32_t b = __byte_perm(j < 2 ? w.x : w.y, 0u, (j & 1) ? 0x4432 : 0x4410);
-                cd[j]            = __dadd_rn(__hiloint2double(0x43300000, (int)b), -kOff);
-            }
+            uint4 w = __ldg(reinterpret_cast<const uint4 *>(sp));
+            const uint32_t ww[4] = {w.x ^ 0x80008000u, w.y ^ 0x80008000u, w.z ^ 0x80008000u, w.w ^ 0x80008000u};
+            cd[0] = splice_low<0x4410>(tmplA, ww[0], -kOff), cd[1] = splice_low<0x4432>(tmplB, ww[0], -kOff);
+            cd[2] = splice_low<0x4410>(tmplA, ww[1], -kOff), cd[3] = splice_low<0x4432>(tmplB, ww[1], -kOff);
+            cd[4] = splice_low<0x4410>(tmplA, ww[2], -kOff), cd[5] = splice_low<0x4432>(tmplB, ww[2], -kOff);
+            cd[6] = splice_low<0x4410>(tmplA, ww[3], -kOff), cd[7] = splice_low<0x4432>(tmplB, ww[3], -kOff);
         }
         if constexpr (DD) {
             const double wx = g8d_qPi2[BE][tbl2][i][0], wy = g8d_qPi2[BE][tbl2][i][1];
@@ -123,9 +137,9 @@ __global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t 
     const double Px = g8d_P[BE][N - 2][0], Py = g8d_P[BE][N - 2][1];
     const int sB = c.sftB[col];
     // sftA has pad256(m) entries, so the (unused) tail rows of the last group may be read safely; row % VEC == 0
-    int16_t sA[VEC];
-    if constexpr (VEC == 4) *reinterpret_cast<uint2 *>(sA) = *reinterpret_cast<const uint2 *>(c.sftA + row);
-    else *reinterpret_cast<uint32_t *>(sA) = *reinterpret_cast<const uint32_t *>(c.sftA + row);
+    __align__(16) int16_t sA[VEC];
+    if constexpr (VEC == 8) *reinterpret_cast<uint4 *>(sA) = *reinterpret_cast<const uint4 *>(c.sftA + row);
+    else *reinterpret_cast<uint2 *>(sA) = *reinterpret_cast<const uint2 *>(c.sftA + row);
     U ab[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
@@ -142,9 +156,26 @@ __global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t 
     const int valid = (int)min((size_t)VEC, c.m - row) * (TR::cplx ? 2 : 1);
     constexpr int PER16 = 16 / sizeof(U); // scalars per 128-bit access
     const bool full = VECIO && valid == NV;
-    U old[NV];
+    // general modes: the scalars first -- beta == 0 means "C is not read" (the BLAS convention cuBLAS follows; the reference's
+    // fma(beta, C, alpha * AB) would turn a stale NaN / Inf in an uninitialised C into a NaN result, inverse_scaling_real.hpp:171-186)
+    U ar = 1, ai = 0, br = 0, bi = 0;
+    bool read_old = (MODE == 1 || MODE == 3);
+    if constexpr (MODE >= 4) {
+        if constexpr (MODE == 5) {
+            const U *pa = reinterpret_cast<const U *>(c.alpha), *pb = reinterpret_cast<const U *>(c.beta);
+            ar = pa[0], br = pb[0];
+            if constexpr (TR::cplx) ai = pa[1], bi = pb[1];
+        } else {
+            ar = (U)hs.ar, ai = (U)hs.ai, br = (U)hs.br, bi = (U)hs.bi;
+        }
+        read_old = !(br == U(0) && bi == U(0));
+    }
+    __align__(16) U old[NV];
     if constexpr (MODE == 1 || MODE == 3 || MODE >= 4) {
-        if (full) {
+        if (!read_old) {
+#pragma unroll
+            for (int j = 0; j < NV; ++j) old[j] = U(0);
+        } else if (full) {
 #pragma unroll
             for (int j = 0; j < NV; j += PER16) *reinterpret_cast<uint4 *>(old + j) = *reinterpret_cast<const uint4 *>(dst + j);
         } else {
@@ -152,7 +183,7 @@ __global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t 
             for (int j = 0; j < NV; ++j) old[j] = (j < valid) ? dst[j] : U(0);
         }
     }
-    U out[NV];
+    __align__(16) U out[NV];
     if constexpr (MODE == 0) {
 #pragma unroll
         for (int j = 0; j < NV; ++j) out[j] = ab[j];
@@ -166,14 +197,6 @@ __global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t 
 #pragma unroll
         for (int j = 0; j < NV; ++j) out[j] = old[j] - ab[j];
     } else {
-        U ar, ai = 0, br, bi = 0;
-        if constexpr (MODE == 5) {
-            const U *pa = reinterpret_cast<const U *>(c.alpha), *pb = reinterpret_cast<const U *>(c.beta);
-            ar = pa[0], br = pb[0];
-            if constexpr (TR::cplx) ai = pa[1], bi = pb[1];
-        } else {
-            ar = (U)hs.ar, ai = (U)hs.ai, br = (U)hs.br, bi = (U)hs.bi;
-        }
         if constexpr (TR::cplx) {
             // Taxpby_scal (template_math.hpp:64-75)
 #pragma unroll

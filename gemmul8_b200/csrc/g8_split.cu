@@ -19,6 +19,10 @@
 // same shuffle tree.
 #include "g8_internal.cuh"
 
+#include <cstdlib>
+#include <mutex>
+#include <set>
+#include <utility>
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
 
@@ -123,11 +127,15 @@ template <typename U> __device__ __forceinline__ int8_t upper_bound_i8(U a, int 
 //
 // x is kept as a binary64 value (it is one: at most 53 significant bits).  Instead of the reference's
 // per-modulus 64-bit mulhi chains (mod.hpp:31-55) we reduce in two levels (gemmul8_b200/tables.py:fast_mod_tables):
-//   level 1 (FP64 pipe, once per group of three moduli):  r = x - M_g * rint(x / M_g), |r| <= 0.501 M_g < 2^24
-//   level 2 (integer pipes, per modulus):  a1 = int(r) + h + K p >= 0;  q = umulhi(a1, ceil(2^32/p)) = floor(a1/p) exactly;
-//                                          s = (a1 - h) - q p  in [-h, h]  -- the symmetric residue, no compare/select.
+//   level 1 (FP64 pipe, once per group of three moduli, M_g < 2^24):
+//       t = fma(x, 1/M_g, 1.5 2^52);  q = t - 1.5 2^52 = rint(x / M_g);  r = fma(-M_g, q, x);  a = int(r + B_g), B_g = (M_g - 1) / 2
+//       B_g = (p - 1) / 2 (mod p) for EVERY member p of the group, so (a mod p) - h is the symmetric residue for all of them.
+//   level 2 (integer pipe, per modulus, TWO instructions):  low = a * ceil(2^32 / p);  s = hi32(low * p) + (-h) = (a mod p) - h
+//       (direct remainder by multiply-high; exact range asserted in tables.py, replayed exhaustively in tests/test_tables.py).
+//   p = 256 (INT8) / 1024 (FP8): x = r + M_0 q exactly and lo32(t) = q mod 2^32, so x mod 2^k = (a_0 - B_0 + M_0 lo32(t)) mod 2^k.
 // The results are the unique symmetric representatives, hence bit-identical to the reference's planes.
-// LARGE (num_moduli > 15): |x| may exceed 2^63, so level 1 first folds x modulo M_g * 2^20.
+// LARGE (num_moduli > 15): |x| may exceed 2^63, so level 1 first folds x modulo M_g * 2^20 (a multiple of 2^k: the power-of-two
+// residue is unchanged).
 // ------------------------------------------------------------------------------------------------
 constexpr double kMagic = 6755399441055744.0; // 1.5 * 2^52: (v + kMagic) - kMagic == rint(v) for |v| < 2^51
 
@@ -150,28 +158,25 @@ __device__ __forceinline__ double group_rem(double x, double M, double invM) {
     const double q = __dadd_rn(__fma_rn(x, invM, kMagic), -kMagic);
     return __fma_rn(-M, q, x);
 }
-template <bool LARGE, int BE> __device__ __forceinline__ double level1(double x, int g) {
+// level 1 of group g: a = int(x mod M_g + B_g) >= 0.  POW2: also x mod 2^32-ish seed of the power-of-two modulus (only its low
+// 8 / 10 bits are meaningful), from group 0.
+template <bool LARGE, int BE, bool POW2> __device__ __forceinline__ int32_t level1(double x, int g, int32_t &pow2) {
     const double M = g8d_grpM[BE][g], invM = g8d_grpInvM[BE][g];
     if constexpr (LARGE) x = group_rem(x, M * g8d_foldMul[BE][0], invM * g8d_foldMul[BE][1]);
-    return group_rem(x, M, invM);
+    const double t = __fma_rn(x, invM, kMagic); // low word = rint(x / M) mod 2^32
+    const double r = __fma_rn(-M, __dadd_rn(t, -kMagic), x);
+    int32_t a      = __double2loint(__dadd_rn(r, g8d_grpBias[BE][g]));
+    if constexpr (POW2) pow2 = a + g8d_grpMint[BE][g] * __double2loint(t) - g8d_grpBiasInt[BE][g];
+    // INT8: the rounding slop of q can leave a slightly negative; one + M_g lifts it (unsigned min picks the non-wrapped one)
+    if constexpr (BE == INT8) a = (int32_t)min((uint32_t)a, (uint32_t)a + (uint32_t)g8d_grpMint[BE][g]);
+    return a;
 }
-// symmetric residue (as int32; the low byte is the int8 plane value) of the level-1 remainder r modulo moduli[idx]
-template <int BE> __device__ __forceinline__ int32_t level2(double r, int idx) {
-    const int32_t a1  = __double2loint(__dadd_rn(r, g8d_mbias[BE][idx]));
-    const uint32_t q  = __umulhi((uint32_t)a1, g8d_mmagic[BE][idx]);
-    // a1 - q * p first (one IMAD: q and a1 in registers, -p the single uniform operand), then - h: avoids re-materialising p in a register
-    uint32_t t;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(q), "r"(0u - (uint32_t)g8d_moduli[BE][idx]), "r"((uint32_t)a1));
-    return (int32_t)t - g8d_mhalf[BE][idx];
-}
-// x mod 1024, symmetric (FP8 modulus index 1; mod.hpp:79-93)
-__device__ __forceinline__ int32_t residue1024(double x) {
-    const int32_t v = __double2loint(__dadd_rn(group_rem(x, 4294967296.0, 1.0 / 4294967296.0), kMagic)) & 1023;
-    return v > 512 ? v - 1024 : v;
-}
-// x mod 256 (only the low byte is meaningful)
-__device__ __forceinline__ int32_t residue256(double x) {
-    return __double2loint(__dadd_rn(group_rem(x, 4294967296.0, 1.0 / 4294967296.0), kMagic));
+// symmetric residue (as int32; the low byte is the int8 plane value) of a (= x + h mod p) modulo moduli[idx]
+template <int BE> __device__ __forceinline__ int32_t level2(int32_t a, int idx) {
+    const uint32_t low = (uint32_t)a * g8d_mmagic[BE][idx];
+    uint32_t s;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(s) : "r"(low), "r"((uint32_t)g8d_moduli[BE][idx]), "r"(0u - (uint32_t)g8d_mhalf[BE][idx]));
+    return (int32_t)s;
 }
 // bytes {a, b, c, d}.b0 -> one 32-bit word
 __device__ __forceinline__ uint32_t pack4(int32_t a, int32_t b, int32_t c, int32_t d) {
@@ -182,71 +187,77 @@ __device__ __forceinline__ int32_t add_wrap(int32_t r, int32_t q, int32_t p) {
     return sym_wrap((int)(int8_t)r + (int)(int8_t)q, p);
 }
 
-// One thread's NV consecutive inner indices of one row -> all planes.  `emit(idx, g, words...)` stores NV/4 words.
-// REAL: x[NV]; planes[0].  CPLX: xr/xi; planes[0..2].
-template <bool LARGE, int NV, bool CPLX>
-__device__ __forceinline__ void split_store(const double (&xr)[NV], const double (&xi)[NV], int num_moduli, int8_t *const (&planes)[3],
+// One thread's NV consecutive inner indices of one row -> all planes.  REAL: x[NV]; planes[0].  CPLX: xr/xi; planes[0..2].
+template <int NW> __device__ __forceinline__ void store_words(int8_t *dst, const uint32_t (&w)[NW]) {
+    if constexpr (NW == 4) *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    else if constexpr (NW == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
+    else *reinterpret_cast<uint32_t *>(dst) = w[0];
+}
+// one level-1 group (FIRST: group 0, which also yields the p = 256 plane) and the planes of its member moduli
+template <bool LARGE, int NV, bool CPLX, bool FIRST>
+__device__ __forceinline__ void split_group(const double (&xr)[NV], const double (&xi)[NV], int g, int num_moduli, int8_t *const (&planes)[3],
                                             size_t plane_stride, size_t off) {
     constexpr int NW = NV / 4;
-    auto store = [&](int8_t *base, int idx, const uint32_t (&w)[NW]) {
-        int8_t *dst = base + (size_t)idx * plane_stride + off;
-        if constexpr (NW == 4) *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-        else if constexpr (NW == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
-        else *reinterpret_cast<uint32_t *>(dst) = w[0];
-    };
-    // modulus 0 (p = 256)
-    {
+    int32_t ar[NV], ai[NV];
+    if constexpr (FIRST) {
+        int32_t zr[NV], zi[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            ar[j] = level1<LARGE, INT8, true>(xr[j], g, zr[j]);
+            if constexpr (CPLX) ai[j] = level1<LARGE, INT8, true>(xi[j], g, zi[j]);
+        }
         uint32_t w0[NW], w1[NW], w2[NW];
 #pragma unroll
         for (int q = 0; q < NW; ++q) {
-            int32_t a[4], b[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                a[j] = residue256(xr[4 * q + j]);
-                if constexpr (CPLX) b[j] = residue256(xi[4 * q + j]);
-            }
-            w0[q] = pack4(a[0], a[1], a[2], a[3]);
+            w0[q] = pack4(zr[4 * q], zr[4 * q + 1], zr[4 * q + 2], zr[4 * q + 3]);
             if constexpr (CPLX) {
-                w1[q] = pack4(b[0], b[1], b[2], b[3]);
-                w2[q] = pack4(add_wrap(a[0], b[0], 256), add_wrap(a[1], b[1], 256), add_wrap(a[2], b[2], 256), add_wrap(a[3], b[3], 256));
+                w1[q] = pack4(zi[4 * q], zi[4 * q + 1], zi[4 * q + 2], zi[4 * q + 3]);
+                w2[q] = pack4(add_wrap(zr[4 * q], zi[4 * q], 256), add_wrap(zr[4 * q + 1], zi[4 * q + 1], 256),
+                              add_wrap(zr[4 * q + 2], zi[4 * q + 2], 256), add_wrap(zr[4 * q + 3], zi[4 * q + 3], 256));
             }
         }
-        store(planes[0], 0, w0);
-        if constexpr (CPLX) store(planes[1], 0, w1), store(planes[2], 0, w2);
-    }
-    const int ngroups = (num_moduli - 1 + 2) / 3;
-    for (int g = 0; g < ngroups; ++g) {
-        double rr[NV], ri[NV];
+        store_words<NW>(planes[0] + off, w0);
+        if constexpr (CPLX) store_words<NW>(planes[1] + off, w1), store_words<NW>(planes[2] + off, w2);
+    } else {
+        int32_t unused;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            rr[j] = level1<LARGE, INT8>(xr[j], g);
-            if constexpr (CPLX) ri[j] = level1<LARGE, INT8>(xi[j], g);
-        }
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            const int idx = 3 * g + 1 + t;
-            if (idx < num_moduli) {
-                const int32_t p = g8d_moduli[INT8][idx];
-                uint32_t w0[NW], w1[NW], w2[NW];
-#pragma unroll
-                for (int q = 0; q < NW; ++q) {
-                    int32_t a[4], b[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        a[j] = level2<INT8>(rr[4 * q + j], idx);
-                        if constexpr (CPLX) b[j] = level2<INT8>(ri[4 * q + j], idx);
-                    }
-                    w0[q] = pack4(a[0], a[1], a[2], a[3]);
-                    if constexpr (CPLX) {
-                        w1[q] = pack4(b[0], b[1], b[2], b[3]);
-                        w2[q] = pack4(add_wrap(a[0], b[0], p), add_wrap(a[1], b[1], p), add_wrap(a[2], b[2], p), add_wrap(a[3], b[3], p));
-                    }
-                }
-                store(planes[0], idx, w0);
-                if constexpr (CPLX) store(planes[1], idx, w1), store(planes[2], idx, w2);
-            }
+            ar[j] = level1<LARGE, INT8, false>(xr[j], g, unused);
+            if constexpr (CPLX) ai[j] = level1<LARGE, INT8, false>(xi[j], g, unused);
         }
     }
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const int idx = 3 * g + 1 + t;
+        if (idx < num_moduli) {
+            uint32_t w0[NW], w1[NW], w2[NW];
+            const int32_t hp = g8d_mhalf[INT8][idx] + g8d_moduli[INT8][idx]; // (Re + Im): sr + si + h + p >= 0, = sr + si + h (mod p)
+#pragma unroll
+            for (int q = 0; q < NW; ++q) {
+                int32_t a[4], b[4], c[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    a[j] = level2<INT8>(ar[4 * q + j], idx);
+                    if constexpr (CPLX) {
+                        b[j] = level2<INT8>(ai[4 * q + j], idx);
+                        c[j] = level2<INT8>(a[j] + b[j] + hp, idx);
+                    }
+                }
+                w0[q] = pack4(a[0], a[1], a[2], a[3]);
+                if constexpr (CPLX) w1[q] = pack4(b[0], b[1], b[2], b[3]), w2[q] = pack4(c[0], c[1], c[2], c[3]);
+            }
+            const size_t po = (size_t)idx * plane_stride + off;
+            store_words<NW>(planes[0] + po, w0);
+            if constexpr (CPLX) store_words<NW>(planes[1] + po, w1), store_words<NW>(planes[2] + po, w2);
+        }
+    }
+}
+template <bool LARGE, int NV, bool CPLX>
+__device__ __forceinline__ void split_store(const double (&xr)[NV], const double (&xi)[NV], int num_moduli, int8_t *const (&planes)[3],
+                                            size_t plane_stride, size_t off) {
+    split_group<LARGE, NV, CPLX, true>(xr, xi, 0, num_moduli, planes, plane_stride, off);
+    const int ngroups = g8d_numGroups[INT8][num_moduli];
+    for (int g = 1; g < ngroups; ++g) split_group<LARGE, NV, CPLX, false>(xr, xi, g, num_moduli, planes, plane_stride, off);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -330,23 +341,35 @@ __device__ __forceinline__ void split_store_f8(const double (&x)[NV], const doub
             emit(planes[2], idx, rs);
         }
     };
-    if (num_moduli > 1) { // modulus index 1: p = 1024
-        int32_t r[NV], ri[NV];
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            r[j] = residue1024(x[j]);
-            if constexpr (CPLX) ri[j] = residue1024(xi[j]);
-            else ri[j] = 0;
-        }
-        emit_all(1, r, ri);
-    }
+    // group 0 = moduli {0, 2}; it also yields modulus index 1 (p = 1024) from the low bits of x (see level1)
     const int ngroups = g8d_numGroups[FP8][num_moduli];
     for (int g = 0; g < ngroups; ++g) {
-        double rr[NV], rri[NV];
+        int32_t ar[NV], ai[NV];
+        if (g == 0) {
+            int32_t r[NV], ri[NV];
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            rr[j] = level1<LARGE, FP8>(x[j], g);
-            if constexpr (CPLX) rri[j] = level1<LARGE, FP8>(xi[j], g);
+            for (int j = 0; j < NV; ++j) {
+                int32_t z;
+                ar[j] = level1<LARGE, FP8, true>(x[j], 0, z);
+                z &= 1023;
+                r[j] = z > 512 ? z - 1024 : z; // symmetric, +512 kept (mod.hpp:79-93)
+                if constexpr (CPLX) {
+                    ai[j] = level1<LARGE, FP8, true>(xi[j], 0, z);
+                    z &= 1023;
+                    ri[j] = z > 512 ? z - 1024 : z;
+                } else {
+                    ai[j] = 0, ri[j] = 0;
+                }
+            }
+            if (num_moduli > 1) emit_all(1, r, ri);
+        } else {
+            int32_t unused;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                ar[j] = level1<LARGE, FP8, false>(x[j], g, unused);
+                if constexpr (CPLX) ai[j] = level1<LARGE, FP8, false>(xi[j], g, unused);
+                else ai[j] = 0;
+            }
         }
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -355,8 +378,8 @@ __device__ __forceinline__ void split_store_f8(const double (&x)[NV], const doub
                 int32_t r[NV], ri[NV];
 #pragma unroll
                 for (int j = 0; j < NV; ++j) {
-                    r[j] = level2<FP8>(rr[j], idx);
-                    if constexpr (CPLX) ri[j] = level2<FP8>(rri[j], idx);
+                    r[j] = level2<FP8>(ar[j], idx);
+                    if constexpr (CPLX) ri[j] = level2<FP8>(ai[j], idx);
                     else ri[j] = 0;
                 }
                 emit_all(idx, r, ri);
@@ -459,13 +482,23 @@ template <typename T> __device__ __forceinline__ T ldg_conj(const T *p, bool con
     return v;
 }
 
-template <typename T, bool LARGE, int MODE, int BE>
+// CACHE: the statistics pass (MODE 1 / 2) parks the row in shared memory so that the operand is read from HBM ONCE; element l lives
+// in 16-byte chunk c = l * sizeof(T) / 16 at physical chunk c ^ ((c >> 3) & 7), which keeps both the element-strided writes of the
+// statistics pass and the 8-consecutive-element reads of the split pass bank-conflict free for all four element types.
+template <typename T> __device__ __forceinline__ int cache_slot(int l) {
+    constexpr int PER = 16 / (int)sizeof(T) > 0 ? 16 / (int)sizeof(T) : 1; // elements per 16-byte chunk (1 for double2)
+    const int c = l / PER;
+    return (c ^ ((c >> 3) & 7)) * PER + (l - c * PER);
+}
+template <typename T, bool LARGE, int MODE, int BE, bool CACHE = false>
 __global__ void __launch_bounds__(256) split_rowcontig_kernel(SplitArgs a) {
     using U       = typename Scalar<T>::U;
     const T *in   = reinterpret_cast<const T *>(a.X) + (size_t)blockIdx.x * a.ld;
     const int row = blockIdx.x;
     const int k   = (int)a.inner;
     __shared__ U s_max[32], s_sum[32];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *cache = reinterpret_cast<T *>(smem_raw); // [k_pad] when CACHE
     int sft;
 
     if constexpr (MODE == 0) {
@@ -475,8 +508,10 @@ __global__ void __launch_bounds__(256) split_rowcontig_kernel(SplitArgs a) {
     } else {
         // thread t visits l = t, t+256, ... in order (find_max.hpp:272-277 / 26-38)
         U amax = 0, sum = 0;
+#pragma unroll 4
         for (int l = threadIdx.x; l < k; l += 256) {
             const T v = __ldg(in + l);
+            if constexpr (CACHE) cache[cache_slot<T>(l)] = v;
             if constexpr (MODE == 1) acc_stats<T>(v, amax, sum);
             else acc_amax<T>(v, amax);
         }
@@ -518,8 +553,17 @@ __global__ void __launch_bounds__(256) split_rowcontig_kernel(SplitArgs a) {
         T v[NV];
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            if (l + j < k) v[j] = ldg_conj(in + l + j, a.conj);
-            else v[j] = T{};
+            if (l + j < k) {
+                if constexpr (CACHE && (MODE == 1 || MODE == 2)) {
+                    v[j] = cache[cache_slot<T>(l + j)]; // l % 8 == 0: the 8 elements are whole, consecutive (swizzled) 16-byte chunks
+                    if constexpr (Scalar<T>::cplx)
+                        if (a.conj) v[j].y = -v[j].y;
+                } else {
+                    v[j] = ldg_conj(in + l + j, a.conj);
+                }
+            } else {
+                v[j] = T{};
+            }
         }
         emit_elements<T, LARGE, (MODE == 3 ? 2 : MODE), NV, BE>(v, sft, a, row_off + l);
     }
@@ -566,38 +610,32 @@ __global__ void __launch_bounds__(1024) stats_rowstrided_kernel(SplitArgs a) {
 //            16-byte store per plane; 8 lanes cover a 128-byte line.
 // MODE 0: residues of trunc(x * 2^-sft); MODE 2: bound plane(s) with s0 = sft (as stored)
 // ------------------------------------------------------------------------------------------------
-template <typename T, bool LARGE, int MODE, int BE>
-__global__ void __launch_bounds__(512) split_rowstrided_kernel(SplitArgs a) {
-    constexpr int TL = 128, NV = 8;               // tile: 32 rows x 128 inner; 16 segments of 8 per row
+constexpr int RS_TL = 128; // row-strided tile: 32 rows x 128 inner; 16 segments of 8 per row
+// load one tile (lane = row, 16 warps stride over l) into XOR-swizzled shared memory; returns nothing, caller syncs
+template <typename T> __device__ __forceinline__ void rowstrided_load_tile(const SplitArgs &a, T *tile, int r0, int l0) {
     constexpr int SW = (sizeof(T) == 16) ? 0 : 1; // swizzle granularity that keeps both phases bank-conflict free
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *tile = reinterpret_cast<T *>(smem_raw); // [TL][32], column index XOR-swizzled by the segment number
-
     const T *X     = reinterpret_cast<const T *>(a.X);
-    const int r0   = blockIdx.x * 32;
-    const int l0   = blockIdx.y * TL;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5; // 16 warps
-
-    {
-        const int r = r0 + lane;
+    const int r    = r0 + lane;
 #pragma unroll
-        for (int j = 0; j < TL / 16; ++j) {
-            const int ll = warp + 16 * j;
-            const int l  = l0 + ll;
-            T v{};
-            if (r < (int)a.rows && l < (int)a.inner) v = ldg_conj(X + (size_t)l * a.ld + r, a.conj);
-            tile[ll * 32 + (lane ^ ((ll >> 3) << SW))] = v;
-        }
+    for (int j = 0; j < RS_TL / 16; ++j) {
+        const int ll = warp + 16 * j;
+        const int l  = l0 + ll;
+        T v{};
+        if (r < (int)a.rows && l < (int)a.inner) v = ldg_conj(X + (size_t)l * a.ld + r, a.conj);
+        tile[ll * 32 + (lane ^ ((ll >> 3) << SW))] = v;
     }
-    __syncthreads();
-
+}
+// thread (rr = t / 16, seg = t % 16) owns 8 consecutive l of one row of the tile and emits one 8-byte store per plane
+template <typename T, bool LARGE, int MODE, int BE>
+__device__ __forceinline__ void rowstrided_emit_tile(const SplitArgs &a, const T *tile, int r0, int l0, int sft) {
+    constexpr int NV = 8;
+    constexpr int SW = (sizeof(T) == 16) ? 0 : 1;
     const int rr  = threadIdx.x >> 4; // 0..31
     const int seg = threadIdx.x & 15; // 8 inner indices each
     const int row = r0 + rr;
     if (row >= (int)a.rows) return;
-    const int sft = (MODE == 0) ? -(int)a.sft[row] : (int)a.sft[row];
     const size_t off = (size_t)row * a.k_pad + l0 + seg * NV;
-
     T v[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
@@ -605,6 +643,93 @@ __global__ void __launch_bounds__(512) split_rowstrided_kernel(SplitArgs a) {
         v[j]         = tile[ll * 32 + (rr ^ (seg << SW))];
     }
     emit_elements<T, LARGE, MODE, NV, BE>(v, sft, a, off);
+}
+
+template <typename T, bool LARGE, int MODE, int BE>
+__global__ void __launch_bounds__(512) split_rowstrided_kernel(SplitArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *tile = reinterpret_cast<T *>(smem_raw); // [TL][32], column index XOR-swizzled by the segment number
+    const int r0 = blockIdx.x * 32, l0 = blockIdx.y * RS_TL;
+    rowstrided_load_tile<T>(a, tile, r0, l0);
+    __syncthreads();
+    const int row = r0 + (threadIdx.x >> 4);
+    if (row >= (int)a.rows) return;
+    const int sft = (MODE == 0) ? -(int)a.sft[row] : (int)a.sft[row];
+    rowstrided_emit_tile<T, LARGE, MODE, BE>(a, tile, r0, l0, sft);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ROW-STRIDED accurate stage (i), fused: amax -> s0 -> bound plane(s) with ONE pass over HBM.
+// A cluster of CL CTAs owns a block of 32 rows; CTA c owns the k-slice of tiles [c * tpc, (c + 1) * tpc).  Phase A: every CTA scans
+// its slice for the per-row max |x| (order-free), the cluster combines the CL x 32 maxima through distributed shared memory.
+// Phase B: every CTA walks its slice AGAIN -- 32 rows x (k / CL) elements, e.g. 256 KB, which it has just pulled into L2 -- and emits
+// the bound plane with s0 = 5 (7) - ilogb(amax).  HBM sees the operand once; the second read is an L2 hit.
+// (Fast mode cannot use this: its round-up sum of squares has a contractual order over ALL of k per (row, l mod 32) class.)
+// ------------------------------------------------------------------------------------------------
+template <typename T, int BE, int CL>
+__global__ void __launch_bounds__(512) accu_stage1_rowstrided_kernel(SplitArgs a, int tiles_per_cta) {
+    using U = typename Scalar<T>::U;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *tile = reinterpret_cast<T *>(smem_raw);
+    __shared__ U s_part[16][33];
+    __shared__ U s_rowmax[32]; // this CTA's maxima, read by the whole cluster
+    __shared__ int s_s0[32];
+    const int r0 = blockIdx.x * 32;
+    const int crank = blockIdx.y; // cluster dims (1, CL, 1): rank == blockIdx.y
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ntiles = (int)(a.k_pad / RS_TL);
+    const int t_begin = crank * tiles_per_cta, t_end = min(ntiles, t_begin + tiles_per_cta);
+
+    // ---- phase A: max |x| of row r0 + lane over this CTA's k-slice ----
+    {
+        const T *X  = reinterpret_cast<const T *>(a.X);
+        const int r = r0 + lane;
+        U amax = 0;
+        if (r < (int)a.rows) {
+            const int l_end = min((int)a.inner, t_end * RS_TL);
+#pragma unroll 8
+            for (int l = t_begin * RS_TL + warp; l < l_end; l += 16) acc_amax<T>(__ldg(X + (size_t)l * a.ld + r), amax);
+        }
+        s_part[warp][lane] = amax;
+        __syncthreads();
+        if (warp == 0) {
+            U m = s_part[0][lane];
+#pragma unroll
+            for (int w = 1; w < 16; ++w) m = max(m, s_part[w][lane]);
+            s_rowmax[lane] = m;
+        }
+    }
+    // every CTA's s_rowmax is complete and visible cluster-wide after this barrier
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp == 0) {
+        U m = 0;
+        const uint32_t local = (uint32_t)__cvta_generic_to_shared(&s_rowmax[lane]);
+#pragma unroll
+        for (int c = 0; c < CL; ++c) {
+            uint32_t remote;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(c));
+            U v;
+            if constexpr (sizeof(U) == 8) asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote));
+            else asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote));
+            m = max(m, v);
+        }
+        const int s0 = accu_s0(m) + (BE == FP8 ? 2 : 0);
+        s_s0[lane]   = s0;
+        if (crank == 0 && r0 + lane < (int)a.rows) a.sft[r0 + lane] = (int16_t)s0;
+    }
+    // remote reads of s_rowmax are done once every CTA has arrived here; nobody exits (or reuses smem) before the matching wait below
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    __syncthreads();
+
+    // ---- phase B: bound plane(s) of the same slice (L2 hits) ----
+    const int s0 = s_s0[threadIdx.x >> 4];
+    for (int t = t_begin; t < t_end; ++t) {
+        rowstrided_load_tile<T>(a, tile, r0, t * RS_TL);
+        __syncthreads();
+        rowstrided_emit_tile<T, false, 2, BE>(a, tile, r0, t * RS_TL, s0);
+        __syncthreads();
+    }
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // accurate mode, stage (iii): sft = -(s0 + floor(fmaf_rd(-0x1.000006p-1f, log2f(float(max)), log2P)))
@@ -626,21 +751,65 @@ __global__ void finalize_accu_shift_kernel(int16_t *__restrict__ sft, const int3
 // |x| can exceed 2^63 (two level-1 folds needed) once num_moduli passes the backend's M threshold (common.hpp:15-27)
 static bool is_large(int backend, int num_moduli) { return num_moduli > thresholds(backend).M; }
 
+// dynamic shared memory beyond 48 KB needs a one-time opt-in per kernel AND per device (never repeated on the launch path)
+static void ensure_smem(const void *kern, size_t smem) {
+    if (smem <= 48 * 1024) return;
+    static std::mutex mu;
+    static std::set<std::pair<const void *, int>> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.insert({kern, dev}).second) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+}
+static int env_flag(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 template <typename T, int MODE, int BE> static void launch_rowcontig(const SplitArgs &a, bool large, cudaStream_t st) {
     const dim3 grid((unsigned)a.rows);
-    if (MODE >= 2 || !large) split_rowcontig_kernel<T, false, MODE, BE><<<grid, 256, 0, st>>>(a);
-    else split_rowcontig_kernel<T, true, MODE, BE><<<grid, 256, 0, st>>>(a);
+    // statistics modes: park the row in shared memory when it fits (<= 64 KB: three blocks per SM) so that HBM is read once
+    static const int cache_pref = env_flag("G8_SPLIT_ROW_CACHE", 1);
+    const size_t row_bytes = a.k_pad * sizeof(T);
+    auto go = [&](auto plain, auto cached) {
+        if ((MODE == 1 || MODE == 2) && cache_pref && row_bytes <= 64 * 1024) {
+            ensure_smem(reinterpret_cast<const void *>(cached), row_bytes);
+            cached<<<grid, 256, row_bytes, st>>>(a);
+        } else {
+            plain<<<grid, 256, 0, st>>>(a);
+        }
+    };
+    if (MODE >= 2 || !large) go(split_rowcontig_kernel<T, false, MODE, BE, false>, split_rowcontig_kernel<T, false, MODE, BE, true>);
+    else go(split_rowcontig_kernel<T, true, MODE, BE, false>, split_rowcontig_kernel<T, true, MODE, BE, true>);
 }
 
 template <typename T, int MODE, int BE> static void launch_rowstrided(const SplitArgs &a, bool large, cudaStream_t st) {
-    const dim3 grid((unsigned)((a.rows + 31) / 32), (unsigned)(a.k_pad / 128));
-    const size_t smem = 128 * 32 * sizeof(T);
+    const dim3 grid((unsigned)((a.rows + 31) / 32), (unsigned)(a.k_pad / RS_TL));
+    const size_t smem = RS_TL * 32 * sizeof(T);
     auto go = [&](auto kern) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ensure_smem(reinterpret_cast<const void *>(kern), smem);
         kern<<<grid, 512, smem, st>>>(a);
     };
     if (MODE == 2 || !large) go(split_rowstrided_kernel<T, false, MODE, BE>);
     else go(split_rowstrided_kernel<T, true, MODE, BE>);
+}
+
+// accurate stage (i) for a row-strided operand in ONE launch (cluster of 8 CTAs per 32-row block), see accu_stage1_rowstrided_kernel
+template <typename T, int BE> static bool launch_accu_stage1_rowstrided(const SplitArgs &a, cudaStream_t st) {
+    constexpr int CL = 8;
+    static const int pref = env_flag("G8_SPLIT_FUSED_ACCU", 1);
+    const int ntiles = (int)(a.k_pad / RS_TL);
+    if (!pref || ntiles < CL) return false; // short k: the two-kernel path is just as good
+    const size_t smem = RS_TL * 32 * sizeof(T);
+    auto kern = accu_stage1_rowstrided_kernel<T, BE, CL>;
+    ensure_smem(reinterpret_cast<const void *>(kern), smem);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((a.rows + 31) / 32), CL), cfg.blockDim = dim3(512), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1, attr[0].val.clusterDim.y = CL, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, a, (ntiles + CL - 1) / CL) == cudaSuccess;
 }
 
 template <typename T, int BE> static void split_typed(const SplitArgs &a, int mode, cudaStream_t st) {
@@ -652,6 +821,7 @@ template <typename T, int BE> static void split_typed(const SplitArgs &a, int mo
         else launch_rowcontig<T, 3, BE>(a, large, st);
     } else {
         const dim3 sgrid((unsigned)((a.rows + 31) / 32)), sblock(32, 32);
+        if (mode == 2 && launch_accu_stage1_rowstrided<T, BE>(a, st)) return;
         if (mode == 1) stats_rowstrided_kernel<T, 1, BE><<<sgrid, sblock, 0, st>>>(a);
         if (mode == 2) stats_rowstrided_kernel<T, 2, BE><<<sgrid, sblock, 0, st>>>(a);
         if (mode >= 2) launch_rowstrided<T, 2, BE>(a, large, st);

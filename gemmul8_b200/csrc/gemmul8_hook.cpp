@@ -153,6 +153,7 @@ struct Fingerprint { // what must be unchanged for cached planes to be valid
     void *poolA = nullptr, *poolB = nullptr;
     size_t m = 0, n = 0, lda = 0, ldb = 0;
     int opA = -1, opB = -1;
+    bool keepA = false, keepB = false; // the workspace layout (shift vectors, accurate-mode bound planes) depends on these
 };
 
 struct Session {
@@ -189,6 +190,7 @@ cublasStatus_t order_streams(Session &s, cudaStream_t now) {
 }
 
 template <typename Fn> Fn native(const char *sym) { return reinterpret_cast<Fn>(dlsym(RTLD_NEXT, sym)); }
+constexpr cublasStatus_t kFallBack = static_cast<cublasStatus_t>(-1); // internal: "run the native routine instead"
 
 // ------------------------------------------------------------------ the emulated call
 cublasStatus_t emulate(const TypeInfo &t, const Policy &p, cublasHandle_t handle, cublasOperation_t opA, cublasOperation_t opB, int m,
@@ -224,9 +226,10 @@ cublasStatus_t emulate(const TypeInfo &t, const Policy &p, cublasHandle_t handle
     now.num_moduli = p.num_moduli, now.k = (size_t)k, now.tag = t.tag, now.fast = p.fast, now.backend = p.backend;
     now.A = A, now.B = B, now.poolA = wA, now.poolB = wB;
     now.m = (size_t)m, now.n = (size_t)n, now.lda = (size_t)lda, now.ldb = (size_t)ldb, now.opA = (int)opA, now.opB = (int)opB;
+    now.keepA = p.keepA, now.keepB = p.keepB;
     const Fingerprint &was = s.last;
     const bool same_core   = was.num_moduli == now.num_moduli && was.k == now.k && was.tag == now.tag && was.fast == now.fast &&
-                           was.backend == now.backend;
+                           was.backend == now.backend && was.keepA == now.keepA && was.keepB == now.keepB;
     const bool reuseA = same_core && p.keepA && was.poolA == now.poolA && was.A == now.A && was.m == now.m && was.lda == now.lda &&
                         was.opA == now.opA;
     const bool reuseB = same_core && p.keepB && was.poolB == now.poolB && was.B == now.B && was.n == now.n && was.ldb == now.ldb &&
@@ -242,13 +245,22 @@ cublasStatus_t emulate(const TypeInfo &t, const Policy &p, cublasHandle_t handle
     d.stream = stream;
     const int code = g8_gemm(&d, nullptr);
     if (code != 0) {
-        std::fprintf(stderr, "[gemmul8 hook] emulated %cGEMM failed with status %d\n", t.tag, code);
-        return code == G8_STATUS_INVALID_VALUE ? CUBLAS_STATUS_INVALID_VALUE
-               : code == G8_STATUS_NOT_SUPPORTED ? CUBLAS_STATUS_NOT_SUPPORTED
-                                                 : CUBLAS_STATUS_EXECUTION_FAILED;
+        s.last = Fingerprint{};
+        // argument / capability rejections leave C untouched: let the caller run the native routine instead of failing the application
+        if (code == G8_STATUS_INVALID_VALUE || code == G8_STATUS_NOT_SUPPORTED || code == G8_STATUS_NO_DEVICE_CODE) return kFallBack;
+        std::fprintf(stderr, "[gemmul8 hook] emulated %cGEMM failed with CUDA status %d\n", t.tag, code);
+        return CUBLAS_STATUS_EXECUTION_FAILED;
     }
     s.last = now;
     return CUBLAS_STATUS_SUCCESS;
+}
+
+// Emulation is attempted only where it is exact and can run: an sm_100a device and k within the accumulation bound of the backend
+// (2^17 for INT8, 2^16 for FP8: include/gemmul8_c.h).  Everything else goes to the native routine, as if the hook were not there.
+bool can_emulate(const Policy &p, int k) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || !g8_device_supported(dev)) return false;
+    return (size_t)k <= (p.backend == G8_BACKEND_FP8 ? (size_t(1) << 16) : (size_t(1) << 17));
 }
 
 template <typename T>
@@ -257,13 +269,14 @@ cublasStatus_t gemm_v2(const TypeInfo &t, cublasHandle_t handle, cublasOperation
     if (m <= 0 || n <= 0 || k <= 0) return CUBLAS_STATUS_SUCCESS;
     if (!A || !B || !C) return CUBLAS_STATUS_INVALID_VALUE;
     const Policy p = read_policy(t);
-    if (!p.emulate) {
-        using Fn = cublasStatus_t (*)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int, const T *, const T *, int,
-                                      const T *, int, const T *, T *, int);
-        Fn fn = native<Fn>(t.native_sym);
-        return fn ? fn(handle, opA, opB, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc) : CUBLAS_STATUS_NOT_INITIALIZED;
+    if (p.emulate && can_emulate(p, k)) {
+        const cublasStatus_t st = emulate(t, p, handle, opA, opB, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+        if (st != kFallBack) return st;
     }
-    return emulate(t, p, handle, opA, opB, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    using Fn = cublasStatus_t (*)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int, const T *, const T *, int,
+                                  const T *, int, const T *, T *, int);
+    Fn fn = native<Fn>(t.native_sym);
+    return fn ? fn(handle, opA, opB, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc) : CUBLAS_STATUS_NOT_INITIALIZED;
 }
 
 } // namespace
@@ -304,7 +317,10 @@ G8_EXPORT cublasStatus_t cublasGemmEx(cublasHandle_t h, cublasOperation_t ta, cu
     }
     if (t) {
         const Policy p = read_policy(*t);
-        if (p.emulate) return emulate(*t, p, h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+        if (p.emulate && can_emulate(p, k)) {
+            const cublasStatus_t st = emulate(*t, p, h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+            if (st != kFallBack) return st;
+        }
     }
     using Fn = cublasStatus_t (*)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int, const void *, const void *,
                                   cudaDataType, int, const void *, cudaDataType, int, const void *, void *, cudaDataType, int,

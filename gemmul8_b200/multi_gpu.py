@@ -202,7 +202,10 @@ def all_to_all(out, inp, group=None, async_op=False):
 class KShardGemm:
     """C[:, slab(rank)] = alpha * sum_r A_r B_r (+ beta * C) for real S/D GEMM, op N/N layout of the local slabs
     (A_r: m x k_local column-major with ld = m; B_r: k_local x n column-major with ld = k_local).
-    n must be a multiple of the world size (each rank reconstructs n / world columns)."""
+    n must be a multiple of the world size (each rank reconstructs n / world columns).
+    Accurate mode is bit-identical to the single-GPU call on the concatenated operands (order-free integer reductions).  Fast mode
+    is NOT guaranteed to be: its round-up sum of squares is reduced per shard and then across ranks, a different order than the
+    single-GPU kernel's, so a shift can differ by one on a floor() boundary (the result then agrees to the emulated precision)."""
 
     def __init__(self, m, n, k_local, num_moduli, fastmode=False, dtype=torch.float64, device=None, variant="residue", stages=None,
                  group=None, pipeline_groups=1):
@@ -212,6 +215,9 @@ class KShardGemm:
         self.W, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if n % self.W:
             raise ValueError("n must be divisible by the world size")
+        if self.W * k_local > 2 ** 17:
+            # |sum| <= K_total * 2^14 must stay below 2^31 for the INT32 partials / the bound product (include/gemmul8.hpp:29)
+            raise ValueError(f"K-sharded path: total K = world * k_local = {self.W * k_local} exceeds 2^17 (INT32 accumulation bound)")
         self.m, self.n, self.k, self.N = m, n, k_local, num_moduli
         self.fast, self.dtype, self.variant = bool(fastmode), dtype, variant
         self.st = stages if stages is not None else CudaStages(dtype, num_moduli, device)
@@ -229,8 +235,10 @@ class KShardGemm:
         G = max(1, min(pipeline_groups, N))
         self.batches = [(i * N // G, (i + 1) * N // G - i * N // G) for i in range(G)]  # (first modulus, count)
         per = n * N * self.m_pad
-        # [modulus][col][row]; the fused variant with <= 4 shards lets the CRT kernel sum the shards and needs no C_mid
-        self.C_mid = None if (variant == "fused" and self.W <= 4) else st.empty(N * self.nc * self.m_pad, torch.int8)
+        # [modulus][col][row]; the fused variant lets the CRT kernel sum the (up to 8) shards itself and needs no C_mid
+        # (G8_MG_SUM_IN_CRT=0 restores the separate residue_sum pass of round 1 for more than 4 shards)
+        sum_in_crt = variant == "fused" and (self.W <= 4 or os.environ.get("G8_MG_SUM_IN_CRT", "1") != "0")
+        self.C_mid = None if sum_in_crt else st.empty(N * self.nc * self.m_pad, torch.int8)
         self.peers = None
         if variant == "fused":
             if self.nc % st.scatter_granularity:
@@ -385,6 +393,75 @@ class KShardGemm:
         return C
 
 
+class ModShardGemm:
+    """Modulus-set sharded multi-GPU emulated GEMM (SURVEY section 8e "modulus-set shard"): every rank holds ALL of A and B, computes
+    the shifts and the residue planes redundantly (no communication, bit-identical on every rank by construction), contracts only ITS
+    subset of the moduli -- 14 moduli over 8 GPUs: 2,2,2,2,2,2,1,1 -- and scatters the residue tiles of column slab o straight into
+    rank o's C_mid through the fused GEMM -> NVLink epilogue; rank o then reconstructs C[:, slab(o)].  No reduction is needed: every
+    (modulus, column) pair has exactly one producer.  The split (and accurate mode's bound GEMM) is replicated, so the scaling is
+    bounded by Amdahl: it is the mode for problems whose K cannot be sharded (K-shard needs the caller to hold K-slabs)."""
+
+    def __init__(self, m, n, k, num_moduli, fastmode=False, dtype=torch.float64, device=None, stages=None, group=None):
+        if dtype not in (torch.float32, torch.float64):
+            raise NotImplementedError("modulus-sharded path: real S/D GEMM only")
+        self.group = group
+        self.W, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.m, self.n, self.k, self.N = m, n, k, num_moduli
+        self.fast, self.dtype = bool(fastmode), dtype
+        self.st = st = stages if stages is not None else CudaStages(dtype, num_moduli, device)
+        if n % self.W or (n // self.W) % st.scatter_granularity:
+            raise ValueError(f"n / world must be a multiple of {st.scatter_granularity} (the scatter is tile-granular)")
+        self.m_pad, self.k_pad, self.n_pad = pad256(m), pad256(k), pad256(n)
+        self.nc = n // self.W
+        self.sizeA, self.sizeB = self.k_pad * self.m_pad, self.k_pad * n
+        N, W = num_moduli, self.W
+        base, extra = divmod(N, W)
+        counts = [base + (1 if r < extra else 0) for r in range(W)]
+        self.u0, self.nu = sum(counts[:self.rank]), counts[self.rank]
+        self.A_lo = st.empty(self.sizeA * N, torch.int8)
+        self.B_lo = st.empty(self.sizeB * N, torch.int8)
+        self.sftA = st.zeros(self.m_pad, torch.int16)
+        self.sftB = st.zeros(self.n_pad, torch.int16)
+        self.peers = st.peer_buffer(N * self.nc * self.m_pad, group)   # my C_mid: [modulus][col in slab][row] int8, filled by all ranks
+        self.C_mid = self.peers.local.view(torch.int8)
+        self.token = st.zeros(1, torch.int32)
+        self.local_out_elems = m * self.nc
+
+    def local_out(self, C):
+        return C[:self.local_out_elems]
+
+    def close(self):
+        if self.peers is not None:
+            self.peers.close()
+            self.peers = None
+
+    def run(self, A, B, C, alpha=1.0, beta=0.0):
+        """A: flat m*k (ld = m), B: flat k*n (ld = k), identical on every rank; C: flat m x (n/world) slab (ld = m)."""
+        st, m, n, k, N, mp, nc = self.st, self.m, self.n, self.k, self.N, self.m_pad, self.nc
+        # every rank has the full K: the shifts come from the very kernels of the single-GPU call (split modes 1 / 2), hence the same bits
+        if self.fast:
+            st.split(True, 0, m, k, A, m, 1, self.sftA, self.A_lo, self.sizeA)
+            st.split(False, 0, n, k, B, k, 1, self.sftB, self.B_lo, self.sizeB)
+        else:
+            st.split(True, 0, m, k, A, m, 2, self.sftA, self.A_lo, self.sizeA)     # s0 + bound planes (aliasing plane 0)
+            st.split(False, 0, n, k, B, k, 2, self.sftB, self.B_lo, self.sizeB)
+            rowmax, colmax = st.zeros(self.m_pad, torch.int32), st.zeros(self.n_pad, torch.int32)
+            st.gemm_bound(self.A_lo, self.sizeA, self.B_lo, self.sizeB, m, n, self.k_pad, rowmax, colmax)
+            st.finalize_shift(self.sftA, rowmax, m)
+            st.finalize_shift(self.sftB, colmax, n)
+            st.split(True, 0, m, k, A, m, 0, self.sftA, self.A_lo, self.sizeA)
+            st.split(False, 0, n, k, B, k, 0, self.sftB, self.B_lo, self.sizeB)
+        # (the previous step's CRT on every rank is ordered before these remote writes by the barrier at the end of that step)
+        if self.nu:
+            st.gemm_scatter(0, self.A_lo[self.u0 * self.sizeA:], self.sizeA, self.B_lo[self.u0 * self.sizeB:], self.sizeB, m, n, self.k_pad,
+                            self.nu, self.peers, self.u0 * nc * mp, nc * mp, mp, first=self.u0)
+        dist.all_reduce(self.token, op=dist.ReduceOp.MAX, group=self.group)   # all producers done: my C_mid is complete
+        r0 = self.rank * nc
+        st.crt(self.C_mid, mp, nc * mp, m, nc, C, m, self.sftA, self.sftB[r0:r0 + nc], alpha, beta)
+        dist.all_reduce(self.token, op=dist.ReduceOp.MAX, group=self.group)   # nobody overwrites a C_mid that is still being read
+        return C
+
+
 class NShardGemm:
     """Column-sharded multi-GPU emulated GEMM (SURVEY section 8e "N-shard"): rank r holds ALL of A (m x k) and the column slab
     B[:, n_r] (k x n_local) and produces C[:, n_r].  No bulk exchange at all: the only cross-rank dependency is the accurate-mode
@@ -410,23 +487,76 @@ class NShardGemm:
     def run(self, A, B, C, alpha=1.0, beta=0.0):
         """A: flat m*k (ld = m), B: flat k*n_local (ld = k), C: flat m*n_local (ld = m); all column-major."""
         st, m, n, k, N, mp = self.st, self.m, self.n, self.k, self.N, self.m_pad
-        amaxA, ssA = st.stats(True, 0, m, k, A, m)
-        amaxB, ssB = st.stats(False, 0, n, k, B, k)
+        # every rank has the full K: the shifts come from the very kernels of the single-GPU call (split modes 1 / 2), hence the same bits
         if self.fast:
-            st.shift_from_stats(amaxA, ssA, 0, self.sftA)
-            st.shift_from_stats(amaxB, ssB, 0, self.sftB)
+            st.split(True, 0, m, k, A, m, 1, self.sftA, self.A_lo, self.sizeA)
+            st.split(False, 0, n, k, B, k, 1, self.sftB, self.B_lo, self.sizeB)
         else:
-            st.shift_from_stats(amaxA, None, 1, self.sftA)
-            st.shift_from_stats(amaxB, None, 1, self.sftB)
-            st.split(True, 0, m, k, A, m, 3, self.sftA, self.A_lo, self.sizeA)     # bound planes (aliasing plane 0)
-            st.split(False, 0, n, k, B, k, 3, self.sftB, self.B_lo, self.sizeB)
+            st.split(True, 0, m, k, A, m, 2, self.sftA, self.A_lo, self.sizeA)     # s0 + bound planes (aliasing plane 0)
+            st.split(False, 0, n, k, B, k, 2, self.sftB, self.B_lo, self.sizeB)
             rowmax, colmax = st.zeros(self.m_pad, torch.int32), st.zeros(self.n_pad, torch.int32)
             st.gemm_bound(self.A_lo, self.sizeA, self.B_lo, self.sizeB, m, n, self.k_pad, rowmax, colmax)
             dist.all_reduce(rowmax, op=dist.ReduceOp.MAX, group=self.group)          # the ONLY collective of this mode
             st.finalize_shift(self.sftA, rowmax, m)
             st.finalize_shift(self.sftB, colmax, n)
-        st.split(True, 0, m, k, A, m, 0, self.sftA, self.A_lo, self.sizeA)
-        st.split(False, 0, n, k, B, k, 0, self.sftB, self.B_lo, self.sizeB)
+            st.split(True, 0, m, k, A, m, 0, self.sftA, self.A_lo, self.sizeA)
+            st.split(False, 0, n, k, B, k, 0, self.sftB, self.B_lo, self.sizeB)
         st.gemm(0, self.A_lo, self.sizeA, self.B_lo, self.sizeB, m, n, self.k_pad, N, self.C_mid, n * mp, mp)
         st.crt(self.C_mid, mp, n * mp, m, n, C, m, self.sftA, self.sftB, alpha, beta)
         return C
+
+
+def verify_against_single_gpu(shard, world, rank, dev, num_moduli, fastmode, variant="fused", m=512, k_local=512):
+    """bench.py --gpus N: before anything is timed, run the sharded path on a reduced problem and compare this rank's column slab with
+    the SINGLE-GPU g8.gemm on the assembled operands (every rank regenerates all slabs from the seeds, so no gather is needed).
+    Accurate mode must match bit for bit; fast mode within 1e-9 (see KShardGemm).  Returns a dict for the bench line."""
+    from . import api as g8api
+    dt = torch.float64
+    n = 256 * world
+    nc = n // world if shard in ("k", "mod") else n
+    seedA = lambda r: 777 + (1000 * r if shard == "k" else 0)
+    seedB = lambda r: 999 + (1000 * r if shard in ("k", "n") else 0)
+    if shard == "k":
+        g = KShardGemm(m, n, k_local, num_moduli, fastmode=fastmode, dtype=dt, device=dev, variant=variant)
+        k_tot = k_local * world
+        A_full = torch.cat([g8api.randmat(m, k_local, dt, phi=0.5, seed=seedA(r), device=dev) for r in range(world)])
+        B_full = torch.cat([g8api.randmat(k_local, n, dt, phi=0.5, seed=seedB(r), device=dev).view(n, k_local) for r in range(world)], dim=1).contiguous().view(-1)
+        A_loc = A_full[rank * m * k_local:(rank + 1) * m * k_local].contiguous()
+        B_loc = g8api.randmat(k_local, n, dt, phi=0.5, seed=seedB(rank), device=dev)
+        n_full, cols = n, slice(rank * nc, (rank + 1) * nc)
+    elif shard == "n":
+        g = NShardGemm(m, n, k_local, num_moduli, fastmode=fastmode, dtype=dt, device=dev)
+        k_tot = k_local
+        A_full = g8api.randmat(m, k_tot, dt, phi=0.5, seed=seedA(0), device=dev)
+        B_full = torch.cat([g8api.randmat(k_tot, n, dt, phi=0.5, seed=seedB(r), device=dev) for r in range(world)])
+        A_loc, B_loc = A_full, g8api.randmat(k_tot, n, dt, phi=0.5, seed=seedB(rank), device=dev)
+        n_full, cols = n * world, slice(rank * n, (rank + 1) * n)
+    else:
+        g = ModShardGemm(m, n, k_local, num_moduli, fastmode=fastmode, dtype=dt, device=dev)
+        k_tot = k_local
+        A_full = g8api.randmat(m, k_tot, dt, phi=0.5, seed=seedA(0), device=dev)
+        B_full = g8api.randmat(k_tot, n, dt, phi=0.5, seed=seedB(0), device=dev)
+        A_loc, B_loc = A_full, B_full
+        n_full, cols = n, slice(rank * nc, (rank + 1) * nc)
+    C_loc = torch.zeros(m * nc, dtype=dt, device=dev)
+    g.run(A_loc, B_loc, C_loc)
+    tot, _, _ = g8api.work_size(m, n_full, k_tot, num_moduli)
+    work = torch.empty(tot, dtype=torch.uint8, device=dev)
+    C_full = torch.zeros(m * n_full, dtype=dt, device=dev)
+    g8api.gemm("N", "N", m, n_full, k_tot, 1.0, A_full, m, B_full, k_tot, 0.0, C_full, m, num_moduli, fastmode, work)
+    torch.cuda.synchronize(dev)
+    want = C_full.view(n_full, m)[cols].reshape(-1)
+    same = bool(torch.equal(want.view(torch.int64), C_loc.view(torch.int64)))
+    rel = float(((want - C_loc).abs().max() / want.abs().max().clamp_min(1e-300)).item())
+    ok = same if not fastmode else rel <= 1e-9
+    flags = torch.tensor([int(ok), int(same)], dtype=torch.int32, device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    relt = torch.tensor([rel], dtype=torch.float64, device=dev)
+    dist.all_reduce(relt, op=dist.ReduceOp.MAX)
+    if hasattr(g, "close"):
+        g.close()
+    res = {"problem": f"{shard}-shard DGEMM {m}x{n_full}x{k_tot} num_moduli={num_moduli} fastmode={int(bool(fastmode))} over {world} GPUs vs single-GPU g8.gemm",
+           "all_ranks_ok": bool(flags[0].item()), "bit_identical_all_ranks": bool(flags[1].item()), "max_rel_diff": float(relt.item())}
+    if not res["all_ranks_ok"]:
+        raise RuntimeError(f"multi-GPU verification FAILED: {res}")
+    return res

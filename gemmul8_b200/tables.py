@@ -160,24 +160,33 @@ def mod_pow2(backend: str):
 
 # ---------------------------------------------------------------------------------------------
 # Tables of the split kernel's two-level modular reduction (our own scheme, no reference counterpart):
-#   level 1: r = x - M_g * rint(x / M_g) in binary64 for groups of three consecutive moduli (product M_g < 2^24),
-#   level 2: per modulus p of the group, with the integer v = r (|v| <= 0.501 M_g):
-#            a1 = v + h + K p  (>= 0),  q = floor(a1 / p) = umulhi(a1, ceil(2^32/p)),  s = (a1 - h) - q p  in [-h, h].
-# `fast_mod_tables` proves the exact-floor condition a1 * (ceil(2^32/p) p - 2^32) < 2^32 for every modulus.
+#   level 1 (binary64, once per group of three (INT8) / two (FP8) moduli with product M_g < 2^24):
+#            t = fma(x, 1/M_g, 1.5 * 2^52); q = t - 1.5 * 2^52 = rint(x / M_g); r = fma(-M_g, q, x)   (|r| <= 0.52 M_g, exact integer)
+#            a = int(r + B_g)  with the ONE group bias  B_g = (M_g - 1) / 2  [+ M_g for FP8]:  since M_g = 0 (mod p) for every member p,
+#            B_g = (p - 1) / 2 = h (mod p) for ALL members at once, i.e. (a mod p) - h is the symmetric residue of x for each of them.
+#            INT8 only: a < 0 (rounding slop of q) is lifted by + M_g:  a = umin(a, a + M_g).
+#   level 2 (32-bit integer pipe, per modulus, TWO instructions; direct remainder by a multiply-high, Lemire-Kaser-Kurz 2019):
+#            low = (a * ceil(2^32 / p)) mod 2^32;   s = hi32(low * p) + (-h)     = (a mod p) - h  in [-h, h]
+#            exact iff a * e < 2^32 with e = ceil(2^32 / p) * p - 2^32 -- `fast_mod_tables` asserts it for the whole range of a
+#            of every modulus, tests/test_tables.py replays the device arithmetic exhaustively.
+#   power-of-two modulus (256 INT8 / 1024 FP8): x = r + M_0 q exactly, and the low word of t IS q mod 2^32, hence
+#            x mod 2^k = (a_0 - B_0 + M_0 * lo32(t)) mod 2^k   -- two integer instructions, no extra floating-point reduction.
 # ---------------------------------------------------------------------------------------------
 MAGIC_RINT = 1.5 * 2.0 ** 52
 
 
 def fast_mod_tables(backend: str = "INT8"):
-    """Groups, group products and per-modulus level-2 constants.  INT8: p_0 = 256 is handled by byte extraction and the
-    other moduli form groups of three; FP8: p_1 = 1024 is handled by masking and the others form groups of two (products
-    must stay below 2^24 so that the level-1 remainder is an exact small integer)."""
+    """Groups, group products / biases and per-modulus level-2 constants.  INT8: p_0 = 256 is recovered from group 0 and the
+    other moduli form groups of three; FP8: p_1 = 1024 likewise and the others form groups of two (products stay below 2^24 so
+    that the level-1 remainder is an exact small integer and the level-2 argument stays inside the multiply-high range)."""
     mods = moduli(backend)
     pow2_idx = 0 if backend == "INT8" else 1
     gsz = 3 if backend == "INT8" else 2
+    lift = backend == "INT8"  # negative a lifted by + M_g (INT8); FP8 has room to add M_g unconditionally
     order = [i for i in range(len(mods)) if i != pow2_idx]
     groups = [order[j:j + gsz] for j in range(0, len(order), gsz)]
-    grpM, magic, half, bias = [], [0] * len(mods), [0] * len(mods), [0.0] * len(mods)
+    grpM, grp_bias = [], []
+    magic, half = [0] * len(mods), [0] * len(mods)
     for gi, members in enumerate(groups):
         # a short last group borrows preceding moduli for its product so that x / M_g stays below 2^51
         span = list(members)
@@ -188,25 +197,27 @@ def fast_mod_tables(backend: str = "INT8"):
         M = 1
         for i in span:
             M *= mods[i]
-        assert 2 ** 13 < M < 2 ** 24
+        assert 2 ** 13 < M < 2 ** 24 and M % 2 == 1
         grpM.append(M)
+        B = (M - 1) // 2 + (0 if lift else M)
+        grp_bias.append(B)
         # |level-1 remainder| <= (0.5 + eps) M with eps = |x / M| * 2^-52 <= 2^-6.6 (x < 2^63, M > 2^17.6): allow 0.52 M
         vmax = int(0.52 * M) + 2
+        amax = vmax + B
+        assert (lift and vmax - B < M) or (not lift and B - vmax >= 0)      # one + M lifts every negative a / a is never negative
         for i in members:
             pm = mods[i]
-            h = pm // 2
-            K = -(-(vmax + h) // pm) + 1
+            assert M % pm == 0 and (B - pm // 2) % pm == 0                   # the group bias is = h (mod p) for every member
             mg = -(-(1 << 32) // pm)  # ceil(2^32 / p)
             e = mg * pm - (1 << 32)
-            a1max = vmax + h + K * pm
-            assert 0 < e <= pm and a1max * e < (1 << 32) and a1max < 2 ** 31, (pm, e, a1max)
-            magic[i], half[i], bias[i] = mg, h, MAGIC_RINT + h + K * pm
+            assert 0 < e <= pm and amax * e < (1 << 32) and amax < 2 ** 31, (pm, e, amax)
+            magic[i], half[i] = mg, pm // 2
     members = [list(g) + [-1] * (gsz - len(g)) for g in groups]
     # number of groups needed for the first n moduli
     ngroups = [0] * (len(mods) + 1)
     for n in range(len(mods) + 1):
         ngroups[n] = sum(1 for g in groups if g[0] < n)
-    return dict(groups=groups, members=members, grpM=grpM, magic=magic, half=half, bias=bias, ngroups=ngroups,
+    return dict(groups=groups, members=members, grpM=grpM, grp_bias=grp_bias, lift=lift, magic=magic, half=half, ngroups=ngroups,
                 fold=20 if backend == "INT8" else 30)
 
 

@@ -32,7 +32,7 @@ enum { G8_OP_N = 0, G8_OP_T = 1, G8_OP_C = 2 };
 
 enum {
     G8_STATUS_SUCCESS        = 0,
-    G8_STATUS_INVALID_VALUE  = 10001, /* bad enum / null pointer / num_moduli out of [2,20] (FP64) or [2,13] (FP32) / k > 2^17 */
+    G8_STATUS_INVALID_VALUE  = 10001, /* bad enum / null pointer / num_moduli out of [2,20] (FP64) or [2,13] (FP32) / k > 2^17 (INT8) or 2^16 (FP8) */
     G8_STATUS_NOT_SUPPORTED  = 10002, /* workspace too small for the scratch a path needs (cannot happen with a g8_work_size()-sized buffer) */
     G8_STATUS_NO_DEVICE_CODE = 10003  /* the sm_100a kernels cannot run on this device: there is NO fallback path */
 };

@@ -16,6 +16,10 @@
 #include <vector>
 
 #include REF_GEMMUL8_HPP
+// the reference harness' own matrix generator (testing/make_matrix.hpp:33-82), included where it lies (-I$(REF)/testing)
+#include <curand_kernel.h>
+#include <type_traits>
+#include "make_matrix.hpp"
 
 namespace {
 cublasLtHandle_t g_lt = nullptr;
@@ -79,24 +83,40 @@ int ref_gemm(int dtype, int backend, int use_lt, int opA, int opB, size_t m, siz
     return 1;
 }
 
-// Plain cuBLASLt s8*s8->s32 TN GEMM (the reference's inner call, matmult.hpp:165-169) for the
-// "practical INT8 ceiling" row in BASELINE.md section 2a.  C[m x n] (ld m) = A^T[k x m] * B[k x n].
-int ref_lt_igemm(size_t m, size_t n, size_t k, const int8_t *A, const int8_t *B, int32_t *C, void *ws, size_t ws_bytes,
-                 void *stream) {
+// Synthetic inputs with the reference harness' generator (testing/make_matrix.hpp:33-82), so that `bench.py --impl reference`
+// needs nothing from the product library.  Column-major rows x cols, ld = rows; synchronises like the harness does.
+int ref_randmat(int dtype, void *X, size_t rows, size_t cols, double phi, unsigned long long seed) {
+    switch (dtype) {
+    case 0: makemat::randmat<float>(rows, cols, static_cast<float *>(X), phi, seed); break;
+    case 1: makemat::randmat<double>(rows, cols, static_cast<double *>(X), phi, seed); break;
+    case 2: makemat::randmat<cuFloatComplex>(rows, cols, static_cast<cuFloatComplex *>(X), phi, seed); break;
+    case 3: makemat::randmat<cuDoubleComplex>(rows, cols, static_cast<cuDoubleComplex *>(X), phi, seed); break;
+    default: return 1;
+    }
+    return (int)cudaGetLastError();
+}
+
+// Plain cuBLASLt TN GEMM exactly as the reference's inner call sets it up (matmult.hpp:41-101,165-169): the "practical tensor
+// ceiling" rows of BASELINE.md section 2a.  backend 0: s8 x s8 -> s32 (COMPUTE_32I), 1: e4m3 x e4m3 -> f32 (COMPUTE_32F).
+// C[m x n] (ld m) = A^T[k x m] * B[k x n]; heuristic algo #0 with the given workspace, descriptors cached per (backend, shape).
+int ref_lt_lowgemm(int backend, size_t m, size_t n, size_t k, const void *A, const void *B, void *C, void *ws, size_t ws_bytes, void *stream) {
     if (!g_lt && cublasLtCreate(&g_lt) != CUBLAS_STATUS_SUCCESS) return 2;
     static cublasLtMatmulDesc_t op = nullptr;
     static cublasLtMatrixLayout_t Ad = nullptr, Bd = nullptr, Cd = nullptr;
     static cublasLtMatmulHeuristicResult_t heur{};
     static size_t cm = 0, cn = 0, ck = 0;
-    if (cm != m || cn != n || ck != k) {
-        if (op) { cublasLtMatrixLayoutDestroy(Ad); cublasLtMatrixLayoutDestroy(Bd); cublasLtMatrixLayoutDestroy(Cd); cublasLtMatmulDescDestroy(op); }
+    static int cb = -1;
+    if (cm != m || cn != n || ck != k || cb != backend) {
+        if (op) { cublasLtMatrixLayoutDestroy(Ad); cublasLtMatrixLayoutDestroy(Bd); cublasLtMatrixLayoutDestroy(Cd); cublasLtMatmulDescDestroy(op); op = nullptr; }
+        const auto lowT = backend == 0 ? CUDA_R_8I : CUDA_R_8F_E4M3;
+        const auto hiT  = backend == 0 ? CUDA_R_32I : CUDA_R_32F;
         cublasOperation_t ta = CUBLAS_OP_T, tb = CUBLAS_OP_N;
-        cublasLtMatmulDescCreate(&op, CUBLAS_COMPUTE_32I, CUDA_R_32I);
+        cublasLtMatmulDescCreate(&op, backend == 0 ? CUBLAS_COMPUTE_32I : CUBLAS_COMPUTE_32F, hiT);
         cublasLtMatmulDescSetAttribute(op, CUBLASLT_MATMUL_DESC_TRANSA, &ta, sizeof(ta));
         cublasLtMatmulDescSetAttribute(op, CUBLASLT_MATMUL_DESC_TRANSB, &tb, sizeof(tb));
-        cublasLtMatrixLayoutCreate(&Ad, CUDA_R_8I, k, m, (int64_t)k);
-        cublasLtMatrixLayoutCreate(&Bd, CUDA_R_8I, k, n, (int64_t)k);
-        cublasLtMatrixLayoutCreate(&Cd, CUDA_R_32I, m, n, (int64_t)m);
+        cublasLtMatrixLayoutCreate(&Ad, lowT, k, m, (int64_t)k);
+        cublasLtMatrixLayoutCreate(&Bd, lowT, k, n, (int64_t)k);
+        cublasLtMatrixLayoutCreate(&Cd, hiT, m, n, (int64_t)m);
         cublasLtMatmulPreference_t pref;
         cublasLtMatmulPreferenceCreate(&pref);
         cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MAX_WORKSPACE_BYTES, &ws_bytes, sizeof(ws_bytes));
@@ -104,10 +124,12 @@ int ref_lt_igemm(size_t m, size_t n, size_t k, const int8_t *A, const int8_t *B,
         cublasLtMatmulAlgoGetHeuristic(g_lt, op, Ad, Bd, Cd, Cd, pref, 1, &heur, &got);
         cublasLtMatmulPreferenceDestroy(pref);
         if (!got) return 4;
-        cm = m; cn = n; ck = k;
+        cm = m; cn = n; ck = k; cb = backend;
     }
-    const int32_t one = 1, zero = 0;
-    cublasStatus_t st = cublasLtMatmul(g_lt, op, &one, A, Ad, B, Bd, &zero, C, Cd, C, Cd, &heur.algo, ws, heur.workspaceSize,
+    const int32_t ione = 1, izero = 0;
+    const float fone = 1.0f, fzero = 0.0f;
+    const void *one = backend == 0 ? (const void *)&ione : (const void *)&fone, *zero = backend == 0 ? (const void *)&izero : (const void *)&fzero;
+    cublasStatus_t st = cublasLtMatmul(g_lt, op, one, A, Ad, B, Bd, zero, C, Cd, C, Cd, &heur.algo, ws, heur.workspaceSize,
                                        static_cast<cudaStream_t>(stream));
     return st == CUBLAS_STATUS_SUCCESS ? 0 : 5;
 }

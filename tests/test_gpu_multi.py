@@ -1,5 +1,7 @@
-"""K-sharded path on real GPUs (needs >= 2 devices; skipped otherwise): NCCL collectives + CUDA stage kernels.
-Accurate mode must equal the single-GPU g8_gemm on the concatenated operands bit for bit (both exchange variants)."""
+"""Multi-GPU paths on real GPUs (need >= 2 devices; skipped otherwise): NCCL collectives + CUDA IPC peer memory + CUDA stage kernels,
+on ALL visible GPUs (2, 4 or 8 ranks -- with more than 4 shards the owner side sums 8 per-shard residue arrays inside the CRT kernel).
+K-shard, accurate mode: bit-identical to the single-GPU g8_gemm on the concatenated operands (all exchange variants).
+N-shard and modulus-set shard: bit-identical in both modes."""
 import os
 import socket
 import sys
@@ -9,6 +11,12 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
+
+
+def _world():
+    import torch
+    n = torch.cuda.device_count()
+    return 8 if n >= 8 else 4 if n >= 4 else 2 if n >= 2 else 0
 
 
 def _free_port():
@@ -43,7 +51,13 @@ def _worker(rank, world, port, q):
                 tot, _, _ = g8.work_size(m, n, K, N)
                 work = torch.empty(tot, dtype=torch.uint8, device=f"cuda:{rank}")
                 g8.gemm("N", "N", m, n, K, 1.0, A, m, B, K, 0.0, Cfull, m, N, fast, work)
-                for variant in ("int32", "residue", "fused"):
+                for variant in ("int32", "residue", "fused", "fused-sumpass"):
+                    # "fused-sumpass": more than 4 shards with the separate residue_sum pass instead of the 8-part CRT kernel
+                    os.environ["G8_MG_SUM_IN_CRT"] = "0" if variant == "fused-sumpass" else "1"
+                    if variant == "fused-sumpass":
+                        if world <= 4:
+                            continue
+                        variant = "fused"
                     plan = multi_gpu.KShardGemm(m, n, kl, N, fastmode=fast, dtype=dtype, device=f"cuda:{rank}", variant=variant)
                     C = torch.zeros(plan.local_out_elems, dtype=dtype, device=f"cuda:{rank}")
                     for _ in range(2 if variant == "fused" else 1):   # the fused variant re-uses peer-mapped receive areas across steps
@@ -112,7 +126,7 @@ def test_nshard_nccl_matches_single_gpu(cuda):
     import torch
     import torch.multiprocessing as mp
 
-    world = min(torch.cuda.device_count(), 2)
+    world = _world()
     if world < 2:
         pytest.skip("needs 2 GPUs")
     ctx = mp.get_context("spawn")
@@ -131,13 +145,73 @@ def test_kshard_nccl_matches_single_gpu(cuda):
     import torch
     import torch.multiprocessing as mp
 
-    world = min(torch.cuda.device_count(), 2)
+    world = _world()
     if world < 2:
         pytest.skip("needs 2 GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+    assert all(ok for _, ok in res), res
+
+
+def _modshard_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import gemmul8_b200 as g8
+        from gemmul8_b200 import multi_gpu
+
+        ok_all = True
+        for dtype, N in ((torch.float64, 14), (torch.float32, 6), (torch.float64, 3)):   # N = 3 < world (8 GPUs): some ranks own no modulus
+            m, n, k = 300, 256 * world, 700
+            A = g8.randmat(m, k, dtype, phi=1.0, seed=41, device=f"cuda:{rank}")
+            B = g8.randmat(k, n, dtype, phi=1.0, seed=42, device=f"cuda:{rank}")
+            for fast in (False, True):
+                Cfull = torch.zeros(m * n, dtype=dtype, device=f"cuda:{rank}")
+                tot, _, _ = g8.work_size(m, n, k, N)
+                work = torch.empty(tot, dtype=torch.uint8, device=f"cuda:{rank}")
+                g8.gemm("N", "N", m, n, k, 1.0, A, m, B, k, 0.0, Cfull, m, N, fast, work)
+                plan = multi_gpu.ModShardGemm(m, n, k, N, fastmode=fast, dtype=dtype, device=f"cuda:{rank}")
+                C = torch.zeros(plan.local_out_elems, dtype=dtype, device=f"cuda:{rank}")
+                for _ in range(2):      # the peer-mapped C_mid is re-used across steps
+                    plan.run(A, B, C)
+                torch.cuda.synchronize()
+                plan.close()
+                nc = n // world
+                want = Cfull.view(n, m)[rank * nc:(rank + 1) * nc].reshape(-1)
+                ok = torch.equal(C, want)            # BOTH modes: shifts and planes are computed redundantly, identically, on every rank
+                ok_all &= ok
+                if not ok:
+                    print(f"rank {rank} modulus-shard mismatch dtype={dtype} N={N} fast={fast}", flush=True)
+        q.put((rank, ok_all))
+    except Exception:
+        q.put((rank, False))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_modshard_nccl_matches_single_gpu(cuda):
+    import torch.multiprocessing as mp
+
+    world = _world()
+    if world < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_modshard_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in range(world)]

@@ -124,6 +124,10 @@ class OracleStages:
         view = self._rows_view(is_A, rows, k, X, ld)
         k_pad = pad256(k)
         pl = planes.numpy()
+        if mode in (1, 2):  # the single-GPU modes: statistics -> fast shift (1) / s0 (2), then the split (1) / the bound plane (2)
+            amax, ss = self.stats(is_A, op, rows, k, X, ld)
+            self.shift_from_stats(amax, ss, 0 if mode == 1 else 1, sft)
+            mode = 0 if mode == 1 else 3
         if mode == 3:
             bar = np.zeros((rows, k_pad), dtype=np.int8)
             fn = self.L.g8o_extract_f if view.dtype == np.float32 else self.L.g8o_extract_d
@@ -194,8 +198,8 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, variant, fast, dtype_name, q):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+def _worker(rank, world, port, variant, fast, dtype_name, q, sum_in_crt="1"):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), G8_MG_SUM_IN_CRT=sum_in_crt)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from gemmul8_b200 import multi_gpu
@@ -303,12 +307,14 @@ def test_nshard_two_ranks_matches_single_process(fast):
         assert ok, f"rank {rank}: C slab differs from the single-process oracle"
 
 
-def test_kshard_fused_eight_ranks():
-    """world_size 8 (the box size): the fused variant takes its > 4-shard branch (separate residue-sum pass before the CRT)"""
+@pytest.mark.parametrize("sum_in_crt", ["1", "0"])
+def test_kshard_fused_eight_ranks(sum_in_crt):
+    """world_size 8 (the box size): the fused variant with 8 shards, summed inside the CRT stage (default) or by the separate
+    residue-sum pass (G8_MG_SUM_IN_CRT=0)"""
     world, port = 8, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, "fused", False, "float64", q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, "fused", False, "float64", q, sum_in_crt)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]
@@ -317,3 +323,54 @@ def test_kshard_fused_eight_ranks():
         assert p.exitcode == 0
     for rank, ok, ok_shift in res:
         assert ok_shift and ok, f"rank {rank}: differs from the single-process oracle"
+
+
+def _modshard_worker(rank, world, port, fast, N, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gemmul8_b200 import multi_gpu
+        from oracle import oracle as O
+
+        rng = np.random.default_rng(44)  # same stream on all ranks: A and B are replicated
+        m, n, k = 29, 4 * world, 70
+        A = ((rng.random((m, k)) - 0.5) * np.exp(rng.standard_normal((m, k))))
+        B = ((rng.random((k, n)) - 0.5) * np.exp(rng.standard_normal((k, n))))
+        tA = torch.from_numpy(np.asfortranarray(A).T.copy().reshape(-1))
+        tB = torch.from_numpy(np.asfortranarray(B).T.copy().reshape(-1))
+        plan = multi_gpu.ModShardGemm(m, n, k, N, fastmode=fast, dtype=torch.float64, stages=OracleStages(np.dtype(np.float64), N))
+        C = torch.zeros(plan.local_out_elems, dtype=torch.float64)
+        for _ in range(2):  # the second step re-uses the peer-mapped C_mid
+            plan.run(tA, tB, C)
+        nc = n // world
+        got = C.numpy().reshape(nc, m).T
+        sA, sB = plan.sftA.numpy()[:m].copy(), plan.sftB.numpy()[:n].copy()
+        ref = O.emulate(A, B, "N", "N", N, fast, sftA=None if not fast else sA, sftB=None if not fast else sB)
+        ok_shift = np.array_equal(ref["sftA"], sA) and np.array_equal(ref["sftB"], sB)
+        ok = np.array_equal(np.ascontiguousarray(got).view(np.uint8), np.ascontiguousarray(ref["C"][:, rank * nc:(rank + 1) * nc]).view(np.uint8))
+        plan.close()
+        q.put((rank, bool(ok), bool(ok_shift)))
+    except Exception as e:
+        q.put((rank, False, False))
+        raise e
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,N,fast", [(2, 14, False), (2, 14, True), (4, 3, False)])
+def test_modshard_matches_single_process(world, N, fast):
+    """modulus-set sharded mode: every rank contracts its subset of the moduli (world = 4, N = 3: one rank owns none) and scatters the
+    residue tiles into the owners' C_mid; the reconstructed slab equals the single-process result"""
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_modshard_worker, args=(r, world, port, fast, N, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, ok_shift in res:
+        assert ok_shift, f"rank {rank}: shifts differ from the single-process oracle"
+        assert ok, f"rank {rank}: C slab differs from the single-process oracle"

@@ -68,26 +68,52 @@ def test_generated_header_is_current():
 
 @pytest.mark.parametrize("be", ["INT8", "FP8"])
 def test_level2_residue_formula_exhaustive(be):
-    """Our split's level-2 step (DESIGN 3.1, g8_split.cu:level2): for a level-1 remainder r with |r| <= 0.52 M_g,
-    a1 = r + h + K p >= 0, q = umulhi(a1, ceil(2^32/p)), s = (a1 - h) - q p must be THE symmetric residue of r mod p.
-    Checked by brute force over the whole admissible range of every modulus (no sampling)."""
+    """Our split's level-2 step (DESIGN 3.1, g8_split.cu:level1/level2): a level-1 remainder r with |r| <= 0.52 M_g becomes
+    a = r + B_g (INT8: lifted by + M_g when negative -- replayed as the device's unsigned min), then for every member p of the group
+    low = (a * ceil(2^32/p)) mod 2^32, s = hi32(low * p) - h must be THE symmetric residue of r mod p (direct remainder by
+    multiply-high).  Checked by brute force over the whole admissible range of every modulus (no sampling)."""
     F = T.fast_mod_tables(be)
     mods = T.moduli(be)
     for gi, members in enumerate(F["groups"]):
-        M = F["grpM"][gi]
+        M, B = F["grpM"][gi], F["grp_bias"][gi]
         vmax = int(0.52 * M) + 2
         r = np.arange(-vmax, vmax + 1, dtype=np.int64)
+        a = (r + B) & 0xFFFFFFFF                                   # the int32 register, viewed as unsigned
+        if F["lift"]:
+            a = np.minimum(a, (a + M) & 0xFFFFFFFF)               # VIADDMNMX.U32: min(a, a + M) picks the non-wrapped value
+        assert a.max() < 2 ** 31 and np.all((a - (r + B)) % M == 0)
         for i in members:
             p, h, mg = mods[i], F["half"][i], F["magic"][i]
-            ibias = int(F["bias"][i] - T.MAGIC_RINT)          # h + K p, the integer part of the DADD bias
-            a1 = r + ibias
-            assert a1.min() >= 0 and a1.max() < 2 ** 31
-            q = (a1 * mg) >> 32                                # umulhi on 32-bit operands
-            s = (a1 - h) - q * p
-            assert np.array_equal(q, a1 // p), (be, p)
-            want = ((r + h) % p) - h                           # symmetric representative in [-h, p - 1 - h]
+            low = (a * mg) & 0xFFFFFFFF                            # IMAD (low 32 bits)
+            s = (((low * p) >> 32) + ((-h) & 0xFFFFFFFF)) & 0xFFFFFFFF   # IMAD.HI.U32 with the addend -h
+            s = np.where(s >= 2 ** 31, s - 2 ** 32, s)             # reinterpret as int32
+            want = ((r + h) % p) - h                               # symmetric representative in [-h, p - 1 - h]
             assert np.array_equal(s, want), (be, p)
             assert s.min() >= -h and s.max() <= p - 1 - h
+
+
+@pytest.mark.parametrize("be", ["INT8", "FP8"])
+def test_power_of_two_residue_from_group0(be):
+    """x mod 256 (INT8) / x mod 1024 (FP8) without a separate reduction: x = r + M_0 q exactly and the low word of
+    t = fma(x, 1/M_0, 1.5 2^52) is q mod 2^32, so the low bits of (a_0 - B_0 + M_0 lo32(t)) are those of x (g8_split.cu:level1)."""
+    F = T.fast_mod_tables(be)
+    M, B = F["grpM"][0], F["grp_bias"][0]
+    bits = 8 if be == "INT8" else 10
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([rng.integers(-2 ** 62, 2 ** 62, size=200000), rng.integers(-2 ** 40, 2 ** 40, size=100000), np.arange(-5000, 5000),
+                         [2 ** 63 - 2 ** 10, -(2 ** 63 - 2 ** 10)]])
+    x = xs.astype(np.float64)                                      # the device holds trunc(a 2^s) as a double
+    t = x * (1.0 / M) + T.MAGIC_RINT                               # one rounding like the FMA: |x / M| < 2^51 keeps the product exact enough
+    q = t - T.MAGIC_RINT
+    # exact replay with Python integers (the numpy line above only picks q; r is computed exactly like the device's FMA does)
+    for xv, tv, qv in zip(x[::97], t[::97], q[::97]):
+        xi, qi = int(xv), int(qv)
+        r = xi - M * qi
+        assert abs(r) <= 0.52 * M + 2
+        qlo = int(np.float64(tv).view(np.uint64)) & 0xFFFFFFFF     # __double2loint(t)
+        a = (r + B) & 0xFFFFFFFF
+        z = (a + M * qlo - B) & 0xFFFFFFFF
+        assert z % (1 << bits) == xi % (1 << bits), (xi, qi)
 
 
 @pytest.mark.parametrize("be", ["INT8", "FP8"])

@@ -1,20 +1,21 @@
 #!/usr/bin/env python3
 """Ragged / extreme shapes, ours against the unmodified reference library on the same GPU (bit identity of the complete C):
 n beyond the reference's 12288-column chunking, tall-skinny, the maximum k = 2^17 (INT8) / 65536 (FP8), non-multiples of every tile size."""
+import json
 import sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-sys.argv = [sys.argv[0], "--quick"]
-src = (ROOT / "tools" / "config_table.py").read_text().split("for fast in (False, True):")[0]
-exec(compile(src, "config_table_prefix", "exec"))
+sys.path.insert(0, str(ROOT / "tools"))
+import refcompare
+
 cases = [("d", 1000, 20000, 3000, 14, 0), ("d", 16384, 1000, 2048, 15, 0), ("d", 257, 129, 131072, 14, 0), ("s", 3001, 777, 5000, 7, 0),
          ("z", 1500, 900, 7000, 12, 0), ("c", 2049, 511, 1025, 6, 0), ("d", 3000, 1500, 65536, 12, 1), ("z", 700, 1300, 2100, 9, 1)]
 bad = 0
 for t, m, n, k, N, be in cases:
     for fast in (False, True):
-        run_case("ODD", t, m, n, k, N, be, fast, phi=0.5, warm=1, reps=2, corner=128)
-        r = rows[-1]
+        r = refcompare.run_case("ODD", t, m, n, k, N, be, fast, phi=0.5, warm=1, reps=2, corner=128)
+        print(json.dumps(r), flush=True)
         ok = r["bit_identical"] or (be == 1 and not fast and abs(r["ours"]["err_max"] - r["reference"]["err_max"]) <= 10 * max(r["reference"]["err_max"], 1e-16))
         bad += 0 if ok else 1
 print("ODD SHAPES:", "all bit-identical (FP8 accurate: within the shift caveat)" if not bad else f"{bad} MISMATCHES")
