@@ -47,7 +47,9 @@ def parse():
     ap.add_argument("--backend", default="int8", choices=["int8", "fp8"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the power / native-DGEMM / tensor-ceiling / weak-K legs")
-    ap.add_argument("--mg-variant", default="fused", choices=["int32", "residue", "fused"])
+    ap.add_argument("--mg-variant", default="fused", choices=["int32", "residue", "fused", "native"],
+                    help="K-shard exchange: int32 / residue = NCCL collectives after the GEMM; fused = GEMM -> NVLink scatter kernel, orchestrated "
+                         "from Python with NCCL for the small vectors; native = the same kernels driven by the C ABI g8_gemm_mg (no NCCL, no Python)")
     ap.add_argument("--mg-shard", default="k", choices=["k", "n", "mod"],
                     help="multi-GPU sharding: k = K-sharded (the north-star path, default), n = column-sharded (every rank holds A and a "
                          "column slab of B / C; no bulk exchange), mod = modulus-set sharded (every rank holds A and B, contracts a subset "
@@ -445,6 +447,8 @@ def main():
             g = multi_gpu.ModShardGemm(m, n, k_loc, N, fastmode=fast, dtype=dt, device=dev)
             g.trace_report = lambda: []
             return g
+        if args.mg_variant == "native":
+            return multi_gpu.NativeKShardGemm(m, n, k_loc, N, fastmode=fast, dtype=dt, device=dev)
         return multi_gpu.KShardGemm(m, n, k_loc, N, fastmode=fast, dtype=dt, device=dev, variant=args.mg_variant)
 
     def barrier():
@@ -501,7 +505,8 @@ def main():
     hB = torch.empty(B.numel(), dtype=dt).pin_memory(); hB.copy_(B)
     hC = torch.empty(out_elems, dtype=dt).pin_memory()
     h2d_bytes, d2h_bytes = int(hA.numel() * 8 + hB.numel() * 8), int(hC.numel() * 8)
-    host_plan = g8.HostGemm(m, n, k_local, dt, N, fast, "N", "N", chunk=1024, device=dev) if (mg is None and be == 0) else None
+    # the repo's public host-buffer API (C ABI g8_gemm_host; csrc/g8_host.cu): both backends
+    host_plan = g8.NativeHostGemm(m, n, k_local, dt, N, fast, "N", "N", chunk=1024, device=dev, backend=be) if mg is None else None
 
     def step_e2e():
         if host_plan is not None:

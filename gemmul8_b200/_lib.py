@@ -54,6 +54,17 @@ SYMBOLS = {
     "g8_peer_free": (c_int, [c_void_p]),
     "g8_stage_stats": (c_int, [c_int, c_int, c_int, c_size_t, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "g8_stage_shift_from_stats": (c_int, [c_void_p, c_void_p, c_size_t, c_uint, c_int, c_void_p, c_void_p]),
+    "g8_host_plan_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_size_t, c_size_t, c_size_t, c_uint, c_int, c_size_t]),
+    "g8_gemm_host": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "g8_host_plan_destroy": (c_int, [c_void_p]),
+    "g8_mg_comm_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_size_t, c_void_p]),
+    "g8_mg_comm_connect": (c_int, [c_void_p, c_void_p]),
+    "g8_mg_comm_barrier": (c_int, [c_void_p, c_void_p]),
+    "g8_mg_comm_status": (c_int, [c_void_p]),
+    "g8_mg_comm_destroy": (c_int, [c_void_p]),
+    "g8_mg_plan_create": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_int, c_int, c_int, c_size_t, c_size_t, c_size_t, c_uint, c_int]),
+    "g8_gemm_mg": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "g8_mg_plan_destroy": (c_int, [c_void_p]),
     "g8_randmat": (c_int, [c_int, c_void_p, c_size_t, c_size_t, c_double, ctypes.c_ulonglong, c_void_p]),
     "g8_version": (ctypes.c_char_p, []),
     "g8_device_supported": (c_int, [c_int]),

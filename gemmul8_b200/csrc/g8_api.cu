@@ -13,7 +13,9 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 namespace g8 {
 
@@ -29,6 +31,7 @@ static unsigned num_mat(int backend, unsigned n) { // table.hpp:69-75
     if (backend == INT8) return n;
     return n <= 6 ? 2 * n : 12 + 3 * (n - 6);
 }
+unsigned num_planes(int backend, unsigned num_moduli) { return num_mat(backend, num_moduli); }
 
 static Sizes sizes(bool cplx, int backend, size_t m, size_t n, size_t k, unsigned N, bool enA, bool enB) {
     Sizes s{};
@@ -87,6 +90,8 @@ static bool device_ok() {
     return v == 1;
 }
 
+SplitArgs make_split_args(int is_A, int op, size_t rows, size_t k, const void *X, size_t ld, unsigned N, int16_t *sft, int8_t *base,
+                          size_t plane_stride, size_t group_stride_planes, int backend);
 static SplitArgs split_args(int is_A, int op, size_t rows, size_t k, const void *X, size_t ld, unsigned N, int16_t *sft,
                             int8_t *base, size_t plane_stride, size_t group_stride_planes, int backend = INT8) {
     SplitArgs a{};
@@ -100,6 +105,154 @@ static SplitArgs split_args(int is_A, int op, size_t rows, size_t k, const void 
     a.conj       = (op == OP_C);
     return a;
 }
+
+// ---- stage 2 for `ncols` columns of op(B): the low-precision products of all moduli + requantisation into C_mid ----
+// Shared by the monolithic call (ncols = n) and the host-buffer pipeline (one column chunk at a time: B_lo / C_mid point at the
+// chunk's first column, their plane strides stay those of the full matrices).
+int contract(const ContractArgs &c, cudaStream_t st) {
+    const unsigned N = c.N;
+    const size_t chunkC = c.m_pad * c.ncols; // elements of one product of this chunk
+    if (c.backend == FP8) {
+        // FP8: 3 piece products per modulus (9 for complex: x the three 3M products, gemmul8_real.hpp:159-180, gemmul8_complex.hpp:163-190).
+        // Every product runs as its own unit on full 256 x 256 tiles (one plane pair per unit: the INT8 kernel's operand re-use and L2
+        // footprint) and leaves its residue mod p as int16 in scratch; one combine pass per batch recombines them into C_mid.
+        // (A 3-accumulators-per-tile kernel, EPI_F8_MOD, avoids the scratch round trip but is limited to 128-row tiles and a 3x larger
+        // L2 working set: measured 1.85 vs 2.95 PFLOP/s for cuBLASLt -- see DESIGN.md.)
+        // Scratch (the reference's C_hi area) holds prods x int16 x m_pad x ncols per modulus: moduli are processed in batches that fit.
+        const int prods      = c.cplx ? 9 : 3;
+        const size_t per_mod = (size_t)prods * sizeof(int16_t) * chunkC;
+        const unsigned batch = (unsigned)std::min<size_t>(N, c.scratch_avail / per_mod);
+        if (batch == 0) return G8_STATUS_NOT_SUPPORTED;
+        int16_t *prod = reinterpret_cast<int16_t *>(c.scratch);
+        for (unsigned u0 = 0; u0 < N; u0 += batch) {
+            const unsigned nu = std::min(batch, N - u0);
+            GemmArgs g{};
+            g.A = c.A_lo, g.B = c.B_lo, g.strideA = c.sizeA, g.strideB = c.sizeB;
+            g.m = c.m, g.n = c.ncols, g.m_pad = c.m_pad, g.k_pad = c.k_pad;
+            g.num_units = (int)nu * prods, g.first_modulus = (int)u0, g.epi = EPI_F8_PROD;
+            g.prods = prods, g.set_stride = (int)c.set_planes;
+            g.out = prod, g.out_stride = chunkC, g.ldc = c.m_pad;
+            if (int e = launch_gemm_tc(g, st)) return e;
+            launch_f8_combine(prod, c.cplx, chunkC, (int)nu, (int)u0,
+                              reinterpret_cast<int16_t *>(c.C_mid) + (c.cplx ? 2 : 1) * (size_t)u0 * c.mid_plane_stride, c.mid_plane_stride, st);
+        }
+    } else if (c.cplx) {
+        // complex INT8: the three 3M products ArBr, AiBi, (Ar+Ai)(Br+Bi) of every modulus run as separate units on full 256 x 256 tiles
+        // (one plane pair per unit, like the real kernel); their symmetric residues go to scratch as int8 and one combine pass per batch
+        // forms {Re, Im} mod p.  The 3-accumulators-per-tile epilogue (EPI_MOD_I8_CPLX: 128-row tiles, three plane pairs live in L2 at
+        // once) measured ~2.0 POP/s against ~3.2 for this path.
+        const size_t per_mod = 3 * chunkC;
+        const unsigned batch = (unsigned)std::min<size_t>(N, c.scratch_avail / per_mod);
+        if (batch == 0) return G8_STATUS_NOT_SUPPORTED;
+        int8_t *prod = c.scratch;
+        for (unsigned u0 = 0; u0 < N; u0 += batch) {
+            const unsigned nu = std::min(batch, N - u0);
+            GemmArgs g{};
+            g.A = c.A_lo, g.B = c.B_lo, g.strideA = c.sizeA, g.strideB = c.sizeB;
+            g.m = c.m, g.n = c.ncols, g.m_pad = c.m_pad, g.k_pad = c.k_pad;
+            g.num_units = (int)nu * 3, g.first_modulus = (int)u0, g.epi = EPI_MOD_I8, g.prods = 3;
+            for (int i = 0; i < 3; ++i) g.groupA[i] = i * (int)c.set_planes + (int)u0, g.groupB[i] = i * (int)c.set_planes + (int)u0;
+            g.out = prod, g.out_stride = chunkC, g.ldc = c.m_pad;
+            if (int e = launch_gemm_tc(g, st)) return e;
+            launch_i8_cplx_combine(prod, chunkC, (int)nu, (int)u0, c.C_mid + 2 * (size_t)u0 * c.mid_plane_stride, c.mid_plane_stride, st);
+        }
+    } else {
+        GemmArgs g{};
+        g.A = c.A_lo, g.B = c.B_lo, g.strideA = c.sizeA, g.strideB = c.sizeB;
+        g.m = c.m, g.n = c.ncols, g.m_pad = c.m_pad, g.k_pad = c.k_pad;
+        g.num_units = (int)N, g.first_modulus = 0, g.epi = EPI_MOD_I8;
+        g.out = c.C_mid, g.out_stride = c.mid_plane_stride, g.ldc = c.m_pad;
+        if (int e = launch_gemm_tc(g, st)) return e;
+    }
+    return 0;
+}
+
+// accurate mode: the bound GEMM over `ncols` columns with the row / column maxima fused into its epilogue (scaling_accu_real.hpp:415-432
+// + :142-226; complex :444-449; FP8 find_max.hpp:82-140).  rowmax accumulates (atomicMax), colmax belongs to these columns.
+int bound_gemm(bool cplx, int backend, const int8_t *A_bound, size_t sizeA, const int8_t *B_bound, size_t sizeB, size_t m, size_t ncols,
+               size_t m_pad, size_t k_pad, size_t k_true, int32_t *rowmax, int32_t *colmax, cudaStream_t st) {
+    GemmArgs g{};
+    g.A = A_bound, g.B = B_bound, g.strideA = sizeA, g.strideB = sizeB;
+    g.m = m, g.n = ncols, g.m_pad = m_pad, g.k_pad = k_pad;
+    g.num_units = 1, g.first_modulus = 0;
+    g.epi = backend == FP8 ? (cplx ? EPI_F8_BOUND_CPLX : EPI_F8_BOUND) : (cplx ? EPI_BOUND_MAX_CPLX : EPI_BOUND_MAX);
+    g.k_true = (int)k_true;
+    g.groupA[0] = 0, g.groupA[1] = 1, g.groupA[2] = 2;
+    g.groupB[0] = 0, g.groupB[1] = 1, g.groupB[2] = 2;
+    if (!cplx) g.groupA[1] = g.groupA[2] = g.groupB[1] = g.groupB[2] = 0;
+    g.ldc = m_pad, g.rowmax = rowmax, g.colmax = colmax;
+    return launch_gemm_tc(g, st);
+}
+
+// ---- helper stream for the B-side preprocessing (one per device, created on first use) ----
+// fork(): the helper stream waits for everything enqueued on the caller's stream so far; join(): the caller's stream waits for the
+// helper.  The fork / launch / join enqueue sequence of one call holds the device's mutex, so that concurrent g8_gemm calls of several
+// host threads cannot interleave their records of the shared events.  The pattern (event-forked side stream joined back before the
+// call returns) is CUDA-graph capturable.  G8_OVERLAP_SIDES=0 keeps everything on the caller's stream.
+struct SideShared {
+    std::mutex mu;
+    cudaStream_t s   = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool ok          = false, tried = false;
+};
+static SideShared &side_shared() {
+    static SideShared per_dev[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return per_dev[dev & 63];
+}
+class SideStream {
+    SideShared *sh_ = nullptr;
+    cudaStream_t main_, use_;
+    bool forked_ = false;
+
+  public:
+    SideStream(cudaStream_t main, bool want) : main_(main), use_(main) {
+        static const bool enabled = [] { const char *e = getenv("G8_OVERLAP_SIDES"); return !(e && e[0] == '0'); }();
+        if (!want || !enabled) return;
+        SideShared &sh = side_shared();
+        sh.mu.lock();
+        if (!sh.tried) {
+            sh.tried = true;
+            sh.ok = cudaStreamCreateWithFlags(&sh.s, cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&sh.fork, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&sh.join, cudaEventDisableTiming) == cudaSuccess;
+            if (!sh.ok) cudaGetLastError();
+        }
+        if (!sh.ok) {
+            sh.mu.unlock();
+            return;
+        }
+        sh_ = &sh, use_ = sh.s;
+        fork();
+    }
+    cudaStream_t stream() const { return use_; }
+    void fork() {
+        if (!sh_ || forked_) return;
+        cudaEventRecord(sh_->fork, main_);
+        cudaStreamWaitEvent(sh_->s, sh_->fork, 0);
+        forked_ = true;
+    }
+    void join() {
+        if (!sh_ || !forked_) return;
+        cudaEventRecord(sh_->join, sh_->s);
+        cudaStreamWaitEvent(main_, sh_->join, 0);
+        forked_ = false;
+    }
+    ~SideStream() {
+        if (!sh_) return;
+        join(); // also on the early error returns: the helper stream never outlives the call un-joined
+        sh_->mu.unlock();
+    }
+    SideStream(const SideStream &) = delete;
+    SideStream &operator=(const SideStream &) = delete;
+};
+
+SplitArgs make_split_args(int is_A, int op, size_t rows, size_t k, const void *X, size_t ld, unsigned N, int16_t *sft, int8_t *base,
+                          size_t plane_stride, size_t group_stride_planes, int backend) {
+    return split_args(is_A, op, rows, k, X, ld, N, sft, base, plane_stride, group_stride_planes, backend);
+}
+bool device_supported_cached() { return device_ok(); }
 
 static int gemm_impl(const g8_gemm_desc &d, double *phase_ns) {
     if (!d.A || !d.B || !d.C || !d.alpha || !d.beta || !d.work) return G8_STATUS_INVALID_VALUE;
@@ -149,94 +302,47 @@ static int gemm_impl(const g8_gemm_desc &d, double *phase_ns) {
     } else if (!(skipA && skipB)) {
         SplitArgs sa = split_args(1, d.op_A, d.m, d.k, d.A, d.lda, N, sftA, A_lo, s.sizeA, groupA_planes, d.backend);
         SplitArgs sb = split_args(0, d.op_B, d.n, d.k, d.B, d.ldb, N, sftB, B_lo, s.sizeB, groupB_planes, d.backend);
+        // The A side and the B side are independent until they meet in a GEMM, and each of their kernels alone leaves HBM half idle
+        // (they are latency / issue bound): the B side runs on a helper stream, forked from and joined back into `st`.
+        SideStream side(st, !skipA && !skipB);
+        cudaStream_t sB = side.stream();
         if (d.fastmode) {
             if (!skipA) launch_split(sa, d.dtype, 1, st);
-            if (!skipB) launch_split(sb, d.dtype, 1, st);
+            if (!skipB) launch_split(sb, d.dtype, 1, sB);
+            side.join();
         } else {
             const size_t need = sizeof(int32_t) * (s.m_pad + s.n_pad);
             if (need > scratch_avail) return G8_STATUS_NOT_SUPPORTED;
             int32_t *rowmax = reinterpret_cast<int32_t *>(scratch), *colmax = rowmax + s.m_pad;
             SplitArgs ea = sa, eb = sb;
             for (int g = 0; g < 3; ++g) ea.planes[g] = A_bound + g * s.sizeA, eb.planes[g] = B_bound + g * s.sizeB;
-            if (!skipA) launch_split(ea, d.dtype, 2, st);
-            if (!skipB) launch_split(eb, d.dtype, 2, st);
             cudaMemsetAsync(rowmax, 0, need, st);
-            GemmArgs g{};
-            g.A = A_bound, g.B = B_bound, g.strideA = s.sizeA, g.strideB = s.sizeB;
-            g.m = d.m, g.n = d.n, g.m_pad = s.m_pad, g.k_pad = s.k_pad;
-            g.num_units = 1, g.first_modulus = 0;
-            g.epi = d.backend == FP8 ? (cplx ? EPI_F8_BOUND_CPLX : EPI_F8_BOUND) : (cplx ? EPI_BOUND_MAX_CPLX : EPI_BOUND_MAX);
-            g.k_true = (int)d.k;
-            g.groupA[0] = 0, g.groupA[1] = 1, g.groupA[2] = 2;
-            g.groupB[0] = 0, g.groupB[1] = 1, g.groupB[2] = 2;
-            if (!cplx) g.groupA[1] = g.groupA[2] = g.groupB[1] = g.groupB[2] = 0;
-            g.ldc = s.m_pad, g.rowmax = rowmax, g.colmax = colmax;
-            if (int e = launch_gemm_tc(g, st)) return e;
+            side.fork();
+            if (!skipA) launch_split(ea, d.dtype, 2, st);
+            if (!skipB) launch_split(eb, d.dtype, 2, sB);
+            side.join();
+            if (int e = bound_gemm(cplx, d.backend, A_bound, s.sizeA, B_bound, s.sizeB, d.m, d.n, s.m_pad, s.k_pad, d.k, rowmax, colmax, st)) return e;
+            side.fork();
             if (!skipA) {
                 launch_finalize_accu_shift(sftA, rowmax, d.m, (int)N, st, d.backend);
                 launch_split(sa, d.dtype, 0, st);
             }
             if (!skipB) {
-                launch_finalize_accu_shift(sftB, colmax, d.n, (int)N, st, d.backend);
-                launch_split(sb, d.dtype, 0, st);
+                launch_finalize_accu_shift(sftB, colmax, d.n, (int)N, sB, d.backend);
+                launch_split(sb, d.dtype, 0, sB);
             }
+            side.join();
         }
     }
     tm.mark(1);
 
     // ---- stage 2: all moduli in one persistent tensor-core launch, mod-p fused ----
-    if (d.k != 0 && d.backend == FP8) {
-        // FP8: 3 piece products per modulus (9 for complex: x the three 3M products, gemmul8_real.hpp:159-180, gemmul8_complex.hpp:163-190).
-        // Every product runs as its own unit on full 256 x 256 tiles (one plane pair per unit: the INT8 kernel's operand re-use and L2
-        // footprint) and leaves its residue mod p as int16 in scratch; one combine pass per batch recombines them into C_mid.
-        // (A 3-accumulators-per-tile kernel, EPI_F8_MOD, avoids the scratch round trip but is limited to 128-row tiles and a 3x larger
-        // L2 working set: measured 1.85 vs 2.95 PFLOP/s for cuBLASLt -- see DESIGN.md.)
-        // Scratch (the reference's C_hi area) holds prods x int16 x m_pad x n per modulus: moduli are processed in batches that fit.
-        const int prods      = cplx ? 9 : 3;
-        const size_t per_mod = (size_t)prods * sizeof(int16_t) * s.sizeC;
-        const unsigned batch = (unsigned)std::min<size_t>(N, scratch_avail / per_mod);
-        if (batch == 0) return G8_STATUS_NOT_SUPPORTED;
-        int16_t *prod = reinterpret_cast<int16_t *>(scratch);
-        for (unsigned u0 = 0; u0 < N; u0 += batch) {
-            const unsigned nu = std::min(batch, N - u0);
-            GemmArgs g{};
-            g.A = A_lo, g.B = B_lo, g.strideA = s.sizeA, g.strideB = s.sizeB;
-            g.m = d.m, g.n = d.n, g.m_pad = s.m_pad, g.k_pad = s.k_pad;
-            g.num_units = (int)nu * prods, g.first_modulus = (int)u0, g.epi = EPI_F8_PROD;
-            g.prods = prods, g.set_stride = (int)groupA_planes;
-            g.out = prod, g.out_stride = s.sizeC, g.ldc = s.m_pad;
-            if (int e = launch_gemm_tc(g, st)) return e;
-            launch_f8_combine(prod, cplx, s.sizeC, (int)nu, (int)u0, reinterpret_cast<int16_t *>(C_mid) + (cplx ? 2 : 1) * (size_t)u0 * s.sizeC, st);
-        }
-    } else if (d.k != 0 && cplx) {
-        // complex INT8: the three 3M products ArBr, AiBi, (Ar+Ai)(Br+Bi) of every modulus run as separate units on full 256 x 256 tiles
-        // (one plane pair per unit, like the real kernel); their symmetric residues go to scratch as int8 and one combine pass per batch
-        // forms {Re, Im} mod p.  The 3-accumulators-per-tile epilogue (EPI_MOD_I8_CPLX: 128-row tiles, three plane pairs live in L2 at
-        // once) measured ~2.0 POP/s against ~3.2 for this path.
-        const size_t per_mod = 3 * s.sizeC;
-        const unsigned batch = (unsigned)std::min<size_t>(N, scratch_avail / per_mod);
-        if (batch == 0) return G8_STATUS_NOT_SUPPORTED;
-        int8_t *prod = scratch;
-        for (unsigned u0 = 0; u0 < N; u0 += batch) {
-            const unsigned nu = std::min(batch, N - u0);
-            GemmArgs g{};
-            g.A = A_lo, g.B = B_lo, g.strideA = s.sizeA, g.strideB = s.sizeB;
-            g.m = d.m, g.n = d.n, g.m_pad = s.m_pad, g.k_pad = s.k_pad;
-            g.num_units = (int)nu * 3, g.first_modulus = (int)u0, g.epi = EPI_MOD_I8, g.prods = 3;
-            for (int i = 0; i < 3; ++i) g.groupA[i] = i * (int)groupA_planes + (int)u0, g.groupB[i] = i * (int)groupB_planes + (int)u0;
-            g.out = prod, g.out_stride = s.sizeC, g.ldc = s.m_pad;
-            if (int e = launch_gemm_tc(g, st)) return e;
-            launch_i8_cplx_combine(prod, s.sizeC, (int)nu, (int)u0, C_mid + 2 * (size_t)u0 * s.sizeC, st);
-        }
-    } else if (d.k != 0) {
-        GemmArgs g{};
-        g.A = A_lo, g.B = B_lo, g.strideA = s.sizeA, g.strideB = s.sizeB;
-        g.m = d.m, g.n = d.n, g.m_pad = s.m_pad, g.k_pad = s.k_pad;
-        g.num_units = (int)N, g.first_modulus = 0;
-        g.epi = d.backend == FP8 ? EPI_F8_MOD : (cplx ? EPI_MOD_I8_CPLX : EPI_MOD_I8);
-        for (int i = 0; i < 3; ++i) g.groupA[i] = cplx ? i * (int)groupA_planes : 0, g.groupB[i] = cplx ? i * (int)groupB_planes : 0;
-        g.out = C_mid, g.out_stride = s.sizeC, g.ldc = s.m_pad;
-        if (int e = launch_gemm_tc(g, st)) return e;
+    if (d.k != 0) {
+        ContractArgs ca{};
+        ca.cplx = cplx, ca.backend = d.backend, ca.N = N, ca.m = d.m, ca.ncols = d.n, ca.m_pad = s.m_pad, ca.k_pad = s.k_pad;
+        ca.A_lo = A_lo, ca.B_lo = B_lo, ca.sizeA = s.sizeA, ca.sizeB = s.sizeB, ca.set_planes = s.num_mat;
+        ca.C_mid = C_mid, ca.mid_plane_stride = s.sizeC, ca.scratch = scratch, ca.scratch_avail = scratch_avail;
+        if (int e = contract(ca, st)) return e;
     }
     tm.mark(2);
 
@@ -257,7 +363,8 @@ __device__ __forceinline__ int32_t f8_recombine(int32_t c0, int32_t c1, int32_t 
     return sq ? sqrtp * (c0 + c1) + c2 : (c0 * 256) + ((c2 - c0 - c1) * 16) + c1;
 }
 template <bool CPLX>
-__global__ void __launch_bounds__(256) f8_combine_kernel(const int16_t *__restrict__ prod, size_t elems_per_unit, int first_modulus, int16_t *__restrict__ C_mid) {
+__global__ void __launch_bounds__(256) f8_combine_kernel(const int16_t *__restrict__ prod, size_t elems_per_unit, int first_modulus, int16_t *__restrict__ C_mid,
+                                                         size_t out_stride) {
     constexpr int NP = CPLX ? 9 : 3;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i * 8 >= elems_per_unit) return;
@@ -281,7 +388,7 @@ __global__ void __launch_bounds__(256) f8_combine_kernel(const int16_t *__restri
             const int32_t b = mod_i32(f8_recombine(get(0, j + 1), get(1, j + 1), get(2, j + 1), sq, sqrtp), p, pinv);
             o[j >> 1]       = (uint32_t)(a & 0xFFFF) | ((uint32_t)b << 16);
         }
-        *reinterpret_cast<uint4 *>(C_mid + (size_t)u * elems_per_unit + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4 *>(C_mid + (size_t)u * out_stride + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
     } else {
         uint32_t o[8];
 #pragma unroll
@@ -293,14 +400,15 @@ __global__ void __launch_bounds__(256) f8_combine_kernel(const int16_t *__restri
             const int32_t re = mod_i32(rr - ii, p, pinv), im = mod_i32(ss - rr - ii, p, pinv);
             o[j]             = (uint32_t)(re & 0xFFFF) | ((uint32_t)im << 16);
         }
-        uint4 *dst = reinterpret_cast<uint4 *>(C_mid + ((size_t)u * elems_per_unit + i * 8) * 2);
+        uint4 *dst = reinterpret_cast<uint4 *>(C_mid + ((size_t)u * out_stride + i * 8) * 2);
         dst[0]     = make_uint4(o[0], o[1], o[2], o[3]);
         dst[1]     = make_uint4(o[4], o[5], o[6], o[7]);
     }
 }
 
 // ---- INT8 backend, complex: 3M recombination of the per-product residues (conv_hi2mid_complex.hpp:46-127); 16 elements per thread ----
-__global__ void __launch_bounds__(256) i8_cplx_combine_kernel(const int8_t *__restrict__ prod, size_t elems_per_unit, int first_modulus, int8_t *__restrict__ C_mid) {
+__global__ void __launch_bounds__(256) i8_cplx_combine_kernel(const int8_t *__restrict__ prod, size_t elems_per_unit, int first_modulus, int8_t *__restrict__ C_mid,
+                                                              size_t out_stride) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i * 16 >= elems_per_unit) return;
     const int u = blockIdx.y, midx = first_modulus + u;
@@ -322,22 +430,24 @@ __global__ void __launch_bounds__(256) i8_cplx_combine_kernel(const int8_t *__re
         }
         o[j >> 1] = word;
     }
-    uint4 *dst = reinterpret_cast<uint4 *>(C_mid + ((size_t)u * elems_per_unit + i * 16) * 2);
+    uint4 *dst = reinterpret_cast<uint4 *>(C_mid + ((size_t)u * out_stride + i * 16) * 2);
     dst[0]     = make_uint4(o[0], o[1], o[2], o[3]);
     dst[1]     = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
-void launch_i8_cplx_combine(const int8_t *prod, size_t elems_per_unit, int num_units, int first_modulus, int8_t *C_mid, cudaStream_t st) {
+void launch_i8_cplx_combine(const int8_t *prod, size_t elems_per_unit, int num_units, int first_modulus, int8_t *C_mid, size_t out_stride,
+                            cudaStream_t st) {
     const size_t groups = elems_per_unit / 16;
     const dim3 grid((unsigned)((groups + 255) / 256), (unsigned)num_units);
-    i8_cplx_combine_kernel<<<grid, 256, 0, st>>>(prod, elems_per_unit, first_modulus, C_mid);
+    i8_cplx_combine_kernel<<<grid, 256, 0, st>>>(prod, elems_per_unit, first_modulus, C_mid, out_stride);
 }
 
-void launch_f8_combine(const int16_t *prod, bool cplx, size_t elems_per_unit, int num_units, int first_modulus, int16_t *C_mid, cudaStream_t st) {
-    const size_t groups = elems_per_unit / 8; // m_pad * n, m_pad % 256 == 0
+void launch_f8_combine(const int16_t *prod, bool cplx, size_t elems_per_unit, int num_units, int first_modulus, int16_t *C_mid, size_t out_stride,
+                       cudaStream_t st) {
+    const size_t groups = elems_per_unit / 8; // m_pad * ncols, m_pad % 256 == 0
     const dim3 grid((unsigned)((groups + 255) / 256), (unsigned)num_units);
-    if (cplx) f8_combine_kernel<true><<<grid, 256, 0, st>>>(prod, elems_per_unit, first_modulus, C_mid);
-    else f8_combine_kernel<false><<<grid, 256, 0, st>>>(prod, elems_per_unit, first_modulus, C_mid);
+    if (cplx) f8_combine_kernel<true><<<grid, 256, 0, st>>>(prod, elems_per_unit, first_modulus, C_mid, out_stride);
+    else f8_combine_kernel<false><<<grid, 256, 0, st>>>(prod, elems_per_unit, first_modulus, C_mid, out_stride);
 }
 
 // ---- K-sharded multi-GPU helpers (no reference counterpart; arithmetic = conv_hi2mid_real.hpp:19-22) ----

@@ -106,7 +106,33 @@ int launch_crt(const CrtArgs &c, int dtype, cudaStream_t st);
 // then {sym((rr - ii) mod p), sym((ss - rr - ii) mod p)} (conv_hi2mid_complex.hpp:130-188).  Output int16 (x 2 for complex).
 // INT8 backend, complex: {re, im} = {sym((rr - ii) mod p), sym((ss - rr - ii) mod p)} (int8 x 2) from the three per-product residue
 // arrays [modulus in batch][rr, ii, ss][m_pad * n] written by EPI_MOD_I8 with prods = 3 (conv_hi2mid_complex.hpp:46-127)
-void launch_i8_cplx_combine(const int8_t *prod, size_t elems_per_unit, int num_units, int first_modulus, int8_t *C_mid, cudaStream_t st);
-void launch_f8_combine(const int16_t *prod, bool cplx, size_t elems_per_unit, int num_units, int first_modulus, int16_t *C_mid, cudaStream_t st);
+// `out_stride`: elements between consecutive moduli of C_mid (== elems_per_unit for the monolithic call, the full m_pad * n when the
+// products cover only a column chunk)
+void launch_i8_cplx_combine(const int8_t *prod, size_t elems_per_unit, int num_units, int first_modulus, int8_t *C_mid, size_t out_stride,
+                            cudaStream_t st);
+void launch_f8_combine(const int16_t *prod, bool cplx, size_t elems_per_unit, int num_units, int first_modulus, int16_t *C_mid, size_t out_stride,
+                       cudaStream_t st);
+
+// ---- orchestration pieces shared by g8_gemm (g8_api.cu), the host-buffer pipeline (g8_host.cu) and the multi-GPU driver (g8_mg.cu) ----
+struct ContractArgs {
+    bool cplx;
+    int backend;
+    unsigned N;
+    size_t m, ncols, m_pad, k_pad;
+    const int8_t *A_lo, *B_lo; // plane bases (B_lo: first column of the chunk)
+    size_t sizeA, sizeB;       // bytes between planes
+    size_t set_planes;         // planes between the Re / Im / Re+Im plane sets (num_mat)
+    int8_t *C_mid;             // first column of the chunk
+    size_t mid_plane_stride;   // ELEMENTS between C_mid planes (m_pad * n of the full matrix)
+    int8_t *scratch;           // per-product residues of the multi-product paths (complex INT8, FP8)
+    size_t scratch_avail;
+};
+int contract(const ContractArgs &c, cudaStream_t st);
+int bound_gemm(bool cplx, int backend, const int8_t *A_bound, size_t sizeA, const int8_t *B_bound, size_t sizeB, size_t m, size_t ncols,
+               size_t m_pad, size_t k_pad, size_t k_true, int32_t *rowmax, int32_t *colmax, cudaStream_t st);
+SplitArgs make_split_args(int is_A, int op, size_t rows, size_t k, const void *X, size_t ld, unsigned N, int16_t *sft, int8_t *base,
+                          size_t plane_stride, size_t group_stride_planes, int backend);
+unsigned num_planes(int backend, unsigned num_moduli); // table.hpp:69-75
+bool device_supported_cached();
 
 } // namespace g8

@@ -1,0 +1,353 @@
+// gemmul8_b200 -- native K-sharded multi-GPU emulated GEMM (include/gemmul8_c.h: g8_mg_comm_*, g8_mg_plan_*, g8_gemm_mg).
+//
+// New work (the reference is single-GPU).  One process per GPU; rank r owns the K-slab op(A)[:, K_r], op(B)[K_r, :]
+// and reconstructs the column slab C[:, n_r].  Everything between the ranks travels over NVLink peer memory (CUDA IPC) through OUR
+// OWN kernels -- no NCCL, no MPI, no Python on this path:
+//   * bulk exchange : the tcgen05 GEMM epilogue scatters its residue tiles straight into the owners' receive areas
+//                     (g8_stage_gemm_scatter: shared memory -> cp.async.bulk -> peer HBM, overlapped with the MMAs of the next tile);
+//   * small vectors : `mg_allreduce_kernel` -- every rank stores its vector into a mailbox slot of every peer, a flag exchange with
+//                     system-scope release / acquire orders the ranks, every rank reduces the slots IN RANK ORDER (so the round-up
+//                     sums of fast mode are identical on every rank, which NCCL does not promise);
+//   * rank barrier  : the same flag exchange without data (`mg_barrier_kernel`).
+// The host only needs a way to pass one 64-byte IPC handle per rank around at start-up (any transport: a pipe, a file, MPI ...).
+//
+// Exactness: |sum| <= K_total * 2^14 < 2^31 requires K_total = world * k_local <= 2^17.  Accurate mode is bit-identical to the
+// single-GPU g8_gemm on the concatenated operands (max and integer sums are order-free); fast mode may differ in a shift on a floor()
+// boundary (its sum of squares is reduced per shard, then across shards), and is then identical on all ranks.
+#include "g8_internal.cuh"
+#include "../../include/gemmul8_c.h"
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace g8 {
+
+constexpr int MG_FLAG_STRIDE = 64;                        // one 64-byte line per source rank
+constexpr size_t MG_HEADER   = 2 * G8_MAX_PEERS * MG_FLAG_STRIDE; // flags | error word
+constexpr unsigned long long MG_TIMEOUT_CYCLES = 40000000000ull; // ~20 s: a dead peer must not hang the GPU for ever
+
+struct MgDev { // what the kernels need (passed by value)
+    int world, rank;
+    char *peer[G8_MAX_PEERS]; // every rank's mailbox as seen from this process (peer[rank] = local)
+    size_t slot_bytes;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// thread `tid` < world: tell rank `tid` that this rank reached `epoch`, then wait until rank `tid` has reached it too
+__device__ __forceinline__ void flag_exchange(const MgDev &d, int tid, uint32_t epoch) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint32_t *>(d.peer[tid] + (size_t)d.rank * MG_FLAG_STRIDE), epoch);
+    const uint32_t *mine = reinterpret_cast<const uint32_t *>(d.peer[d.rank] + (size_t)tid * MG_FLAG_STRIDE);
+    const unsigned long long t0 = clock64();
+    // epochs only grow; "reached or passed" (a peer may already be one collective ahead); wrap-around safe comparison
+    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+        if (clock64() - t0 > MG_TIMEOUT_CYCLES) {
+            *reinterpret_cast<volatile uint32_t *>(d.peer[d.rank] + G8_MAX_PEERS * MG_FLAG_STRIDE) = 1u; // error word
+            break;
+        }
+    }
+}
+
+__global__ void mg_barrier_kernel(MgDev d, uint32_t epoch) {
+    if ((int)threadIdx.x < d.world) flag_exchange(d, threadIdx.x, epoch);
+}
+
+// OP 0: max, 1: sum (rank order 0, 1, ... on EVERY rank -> identical bits everywhere)
+template <typename T, int OP> __global__ void __launch_bounds__(1024) mg_allreduce_kernel(MgDev d, const T *__restrict__ src, T *__restrict__ out, int count, uint32_t epoch) {
+    const size_t data0 = MG_HEADER + (size_t)(epoch & 1u) * d.world * d.slot_bytes; // double-buffered by the parity of the epoch
+    // 1. my vector -> slot [rank] of every peer's mailbox (remote stores over NVLink; own mailbox included)
+    for (int o = 0; o < d.world; ++o) {
+        T *dst = reinterpret_cast<T *>(d.peer[(d.rank + o) % d.world] + data0 + (size_t)d.rank * d.slot_bytes);
+        for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    // 2. all ranks have delivered
+    if ((int)threadIdx.x < d.world) flag_exchange(d, threadIdx.x, epoch);
+    __syncthreads();
+    // 3. reduce the slots of my own mailbox
+    const char *base = d.peer[d.rank] + data0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        T acc = reinterpret_cast<const volatile T *>(base)[i];
+        for (int o = 1; o < d.world; ++o) {
+            const T v = reinterpret_cast<const volatile T *>(base + (size_t)o * d.slot_bytes)[i];
+            if constexpr (OP == 0) acc = v > acc ? v : acc;
+            else acc = acc + v;
+        }
+        out[i] = acc;
+    }
+}
+
+struct MgComm {
+    int world = 0, rank = 0, device = 0;
+    size_t slot_bytes = 0, bytes = 0;
+    char *local = nullptr;
+    char *peer[G8_MAX_PEERS] = {};
+    bool connected = false;
+    uint32_t epoch = 0; // every rank issues the same sequence of collectives
+    MgDev dev() const {
+        MgDev d{};
+        d.world = world, d.rank = rank, d.slot_bytes = slot_bytes;
+        for (int o = 0; o < world; ++o) d.peer[o] = peer[o];
+        return d;
+    }
+};
+
+static int comm_barrier(MgComm &c, cudaStream_t st) {
+    mg_barrier_kernel<<<1, 32, 0, st>>>(c.dev(), ++c.epoch);
+    return (int)cudaGetLastError();
+}
+template <typename T, int OP> static int comm_allreduce(MgComm &c, const T *src, T *out, size_t count, cudaStream_t st) {
+    if (count * sizeof(T) > c.slot_bytes) return G8_STATUS_NOT_SUPPORTED;
+    if (count == 0) return 0;
+    mg_allreduce_kernel<T, OP><<<1, 1024, 0, st>>>(c.dev(), src, out, (int)count, ++c.epoch);
+    return (int)cudaGetLastError();
+}
+
+struct MgPlan {
+    MgComm *comm = nullptr;
+    int dtype = F64, opA = OP_N, opB = OP_N, fast = 0;
+    size_t m = 0, n = 0, k = 0, m_pad = 0, k_pad = 0, n_pad = 0, nc = 0, sizeA = 0, sizeB = 0;
+    unsigned N = 0;
+    int8_t *A_lo = nullptr, *B_lo = nullptr;
+    int16_t *sftA = nullptr, *sftB = nullptr;
+    double *stat = nullptr;   // amax[m + n] | sumsq[m + n] | reduced copies
+    int32_t *maxes = nullptr; // rowmax[m_pad] | colmax[n_pad] (input of the MAX all-reduce) | reduced copy
+    char *recv = nullptr;     // my receive area: [src rank][modulus][col in slab][row] int8, then (accurate) [src rank][col][row] int32
+    size_t recv_bytes = 0, cbar_off = 0;
+    char *peer_recv[G8_MAX_PEERS] = {};
+};
+
+#define G8_TRY(x)                              \
+    do {                                       \
+        const int _e = (int)(x);               \
+        if (_e != 0) return _e;                \
+    } while (0)
+
+static void plan_free(MgPlan *p) {
+    if (!p) return;
+    for (void *q : {(void *)p->A_lo, (void *)p->B_lo, (void *)p->sftA, (void *)p->sftB, (void *)p->stat, (void *)p->maxes})
+        if (q) cudaFree(q);
+    if (p->comm)
+        for (int o = 0; o < p->comm->world; ++o)
+            if (o != p->comm->rank && p->peer_recv[o]) cudaIpcCloseMemHandle(p->peer_recv[o]);
+    if (p->recv) cudaFree(p->recv);
+    delete p;
+}
+
+// all ranks contribute `bytes` (<= slot) of host data, every rank gets all of them in rank order (start-up only: synchronises)
+static int comm_exchange_host(MgComm &c, const void *mine, size_t bytes, void *all) {
+    if (bytes > c.slot_bytes || bytes % 4) return G8_STATUS_INVALID_VALUE;
+    uint32_t *d_in = nullptr, *d_out = nullptr;
+    const size_t words = bytes / 4, W = (size_t)c.world;
+    G8_TRY(cudaMalloc(&d_in, W * bytes));
+    G8_TRY(cudaMalloc(&d_out, W * bytes));
+    cudaMemset(d_in, 0, W * bytes);
+    cudaMemcpy(reinterpret_cast<char *>(d_in) + (size_t)c.rank * bytes, mine, bytes, cudaMemcpyHostToDevice);
+    int e = 0;
+    // gather == MAX all-reduce of a vector that is zero outside this rank's section (handles are arbitrary bits: reduce as uint32)
+    for (size_t off = 0; off < W * words && !e; off += c.slot_bytes / 4) {
+        const size_t cnt = std::min(c.slot_bytes / 4, W * words - off);
+        e = comm_allreduce<uint32_t, 0>(c, d_in + off, d_out + off, cnt, nullptr);
+    }
+    if (!e) e = (int)cudaMemcpy(all, d_out, W * bytes, cudaMemcpyDeviceToHost);
+    cudaFree(d_in), cudaFree(d_out);
+    return e;
+}
+
+static int plan_create(MgPlan **out, MgComm *c, int dtype, int opA, int opB, size_t m, size_t n, size_t k_local, unsigned N, int fast) {
+    if (!out || !c || !c->connected || (dtype != F32 && dtype != F64) || opA < 0 || opA > 2 || opB < 0 || opB > 2) return G8_STATUS_INVALID_VALUE;
+    if (N < 2 || N > G8_MAX_MODULI || m == 0 || n == 0 || k_local == 0) return G8_STATUS_INVALID_VALUE;
+    const size_t W = (size_t)c->world;
+    if (n % W || (n / W) % 256) return G8_STATUS_INVALID_VALUE;              // the scatter hands whole 256-column tiles to one owner
+    if (W * k_local > (size_t(1) << 17)) return G8_STATUS_INVALID_VALUE;       // INT32 accumulation bound over the TOTAL K
+    if (!device_supported_cached()) return G8_STATUS_NO_DEVICE_CODE;
+    MgPlan *p = new (std::nothrow) MgPlan();
+    if (!p) return (int)cudaErrorMemoryAllocation;
+    p->comm = c, p->dtype = dtype, p->opA = opA, p->opB = opB, p->fast = fast, p->m = m, p->n = n, p->k = k_local, p->N = N;
+    p->m_pad = pad256(m), p->k_pad = pad256(k_local), p->n_pad = pad256(n), p->nc = n / W;
+    p->sizeA = p->k_pad * p->m_pad, p->sizeB = p->k_pad * n;
+    if ((m + n) * sizeof(double) > c->slot_bytes || (p->m_pad + p->n_pad) * sizeof(int32_t) > c->slot_bytes) {
+        delete p;
+        return G8_STATUS_NOT_SUPPORTED; // mailbox slots too small for this problem: create the communicator with a larger max_vector_bytes
+    }
+    auto fail = [&](int code) {
+        plan_free(p);
+        return code;
+    };
+#define G8_ALLOC(ptr, bytes) \
+    if (cudaMalloc(reinterpret_cast<void **>(&(ptr)), (bytes)) != cudaSuccess) return fail((int)cudaErrorMemoryAllocation)
+    G8_ALLOC(p->A_lo, p->sizeA * N);
+    G8_ALLOC(p->B_lo, p->sizeB * N);
+    G8_ALLOC(p->sftA, sizeof(int16_t) * p->m_pad);
+    G8_ALLOC(p->sftB, sizeof(int16_t) * p->n_pad);
+    G8_ALLOC(p->stat, sizeof(double) * 4 * (m + n));
+    G8_ALLOC(p->maxes, sizeof(int32_t) * 2 * (p->m_pad + p->n_pad));
+#undef G8_ALLOC
+    cudaMemset(p->sftA, 0, sizeof(int16_t) * p->m_pad), cudaMemset(p->sftB, 0, sizeof(int16_t) * p->n_pad);
+    const size_t per = (size_t)N * n * p->m_pad; // W shards x N moduli x nc columns x m_pad rows (int8)
+    p->cbar_off   = per;
+    p->recv_bytes = per + (fast ? 0 : sizeof(int32_t) * W * p->nc * p->m_pad);
+    unsigned char handle[64];
+    if (int e = g8_peer_alloc(p->recv_bytes, reinterpret_cast<void **>(&p->recv), handle)) return fail(e);
+    std::vector<unsigned char> all(64 * W);
+    if (int e = comm_exchange_host(*c, handle, 64, all.data())) return fail(e);
+    for (size_t o = 0; o < W; ++o) {
+        if ((int)o == c->rank) {
+            p->peer_recv[o] = p->recv;
+            continue;
+        }
+        void *q = nullptr;
+        if (int e = g8_peer_open(all.data() + 64 * o, &q)) return fail(e);
+        p->peer_recv[o] = static_cast<char *>(q);
+    }
+    *out = p;
+    return 0;
+}
+
+static int run(MgPlan &p, const void *alpha, const void *A, size_t lda, const void *B, size_t ldb, const void *beta, void *C, size_t ldc, cudaStream_t st) {
+    MgComm &c = *p.comm;
+    const size_t m = p.m, n = p.n, k = p.k, W = (size_t)c.world, nc = p.nc, mp = p.m_pad;
+    const unsigned N = p.N;
+    if (!alpha || !beta || !A || !B || !C) return G8_STATUS_INVALID_VALUE;
+    double *amax = p.stat, *ss = p.stat + (m + n), *amax_r = p.stat + 2 * (m + n), *ss_r = p.stat + 3 * (m + n);
+    void *pst = st;
+
+    // ---- shifts from GLOBAL row statistics ----
+    G8_TRY(g8_stage_stats(p.dtype, 1, p.opA, m, k, A, lda, amax, ss, pst));
+    G8_TRY(g8_stage_stats(p.dtype, 0, p.opB, n, k, B, ldb, amax + m, ss + m, pst));
+    G8_TRY((comm_allreduce<double, 0>(c, amax, amax_r, m + n, st)));
+    if (p.fast) {
+        G8_TRY((comm_allreduce<double, 1>(c, ss, ss_r, m + n, st)));
+        G8_TRY(g8_stage_shift_from_stats(amax_r, ss_r, m, N, 0, p.sftA, pst));
+        G8_TRY(g8_stage_shift_from_stats(amax_r + m, ss_r + m, n, N, 0, p.sftB, pst));
+    } else {
+        // accurate: s0 from the global max, bound planes (aliasing plane 0), INT32 bound partial scattered to the owners, slab maxima
+        // of the SUM over the shards, MAX all-reduce of [row maxima | column maxima], final shifts
+        G8_TRY(g8_stage_shift_from_stats(amax_r, nullptr, m, N, 1, p.sftA, pst));
+        G8_TRY(g8_stage_shift_from_stats(amax_r + m, nullptr, n, N, 1, p.sftB, pst));
+        G8_TRY(g8_stage_split(p.dtype, 1, p.opA, m, k, A, lda, N, 3, p.sftA, p.A_lo, p.sizeA, N, pst));
+        G8_TRY(g8_stage_split(p.dtype, 0, p.opB, n, k, B, ldb, N, 3, p.sftB, p.B_lo, p.sizeB, N, pst));
+        const size_t slab = nc * mp;
+        void *tbl[G8_MAX_PEERS];
+        for (size_t o = 0; o < W; ++o) tbl[o] = p.peer_recv[o] + p.cbar_off + sizeof(int32_t) * (size_t)c.rank * slab;
+        G8_TRY(g8_stage_gemm_scatter(1 /*raw int32*/, p.A_lo, p.sizeA, p.B_lo, p.sizeB, m, n, p.k_pad, 1, 0, tbl, (int)W, c.rank, 0, mp, pst));
+        G8_TRY(comm_barrier(c, st));
+        int32_t *mx = p.maxes, *mx_r = p.maxes + (p.m_pad + p.n_pad);
+        G8_TRY(cudaMemsetAsync(mx, 0, sizeof(int32_t) * (p.m_pad + p.n_pad), st));
+        G8_TRY(g8_stage_maxabs_i32_parts(reinterpret_cast<const int32_t *>(p.recv + p.cbar_off), (int)W, slab, m, nc, mp, mx, mx + p.m_pad + (size_t)c.rank * nc, pst));
+        G8_TRY((comm_allreduce<int32_t, 0>(c, mx, mx_r, p.m_pad + p.n_pad, st)));
+        G8_TRY(g8_stage_finalize_shift(p.sftA, mx_r, m, N, pst));
+        G8_TRY(g8_stage_finalize_shift(p.sftB, mx_r + p.m_pad, n, N, pst));
+    }
+
+    // ---- local split with the global shifts, contraction fused with the exchange, owner-side sum + CRT ----
+    G8_TRY(g8_stage_split(p.dtype, 1, p.opA, m, k, A, lda, N, 0, p.sftA, p.A_lo, p.sizeA, N, pst));
+    G8_TRY(g8_stage_split(p.dtype, 0, p.opB, n, k, B, ldb, N, 0, p.sftB, p.B_lo, p.sizeB, N, pst));
+    {
+        void *tbl[G8_MAX_PEERS];
+        for (size_t o = 0; o < W; ++o) tbl[o] = p.peer_recv[o] + (size_t)c.rank * N * nc * mp;
+        G8_TRY(g8_stage_gemm_scatter(0 /*residues mod p*/, p.A_lo, p.sizeA, p.B_lo, p.sizeB, m, n, p.k_pad, (int)N, 0, tbl, (int)W, c.rank, nc * mp, mp, pst));
+    }
+    G8_TRY(comm_barrier(c, st)); // every rank's tiles have landed (kernel completion + system-scope release / acquire)
+    G8_TRY(g8_stage_crt_parts(p.dtype, p.recv, (int)W, (size_t)N * nc * mp, mp, nc * mp, m, nc, N, C, ldc, p.sftA, p.sftB + (size_t)c.rank * nc, alpha, beta, pst));
+    // (the next call's first all-reduce orders every rank's CRT before anybody's next scatter into the receive areas)
+    return (int)cudaPeekAtLastError();
+}
+
+} // namespace g8
+
+using namespace g8;
+
+extern "C" {
+
+__attribute__((visibility("default"))) int g8_mg_comm_create(g8_mg_comm **comm, int world, int rank, size_t max_vector_bytes, void *handle64) {
+    if (!comm || !handle64 || world < 1 || world > G8_MAX_PEERS || rank < 0 || rank >= world) return G8_STATUS_INVALID_VALUE;
+    MgComm *c = new (std::nothrow) MgComm();
+    if (!c) return (int)cudaErrorMemoryAllocation;
+    c->world = world, c->rank = rank;
+    cudaGetDevice(&c->device);
+    c->slot_bytes = std::max<size_t>((max_vector_bytes + 255) / 256 * 256, 4096);
+    c->bytes      = MG_HEADER + 2 * (size_t)world * c->slot_bytes;
+    if (int e = g8_peer_alloc(c->bytes, reinterpret_cast<void **>(&c->local), handle64)) {
+        delete c;
+        return e;
+    }
+    cudaMemset(c->local, 0, c->bytes);
+    cudaDeviceSynchronize();
+    c->peer[rank] = c->local;
+    *comm = reinterpret_cast<g8_mg_comm *>(c);
+    return 0;
+}
+
+__attribute__((visibility("default"))) int g8_mg_comm_connect(g8_mg_comm *comm, const void *handles) {
+    MgComm *c = reinterpret_cast<MgComm *>(comm);
+    if (!c || !handles || c->connected) return G8_STATUS_INVALID_VALUE;
+    for (int o = 0; o < c->world; ++o) {
+        if (o == c->rank) continue;
+        void *q = nullptr;
+        if (int e = g8_peer_open(static_cast<const char *>(handles) + 64 * (size_t)o, &q)) return e;
+        c->peer[o] = static_cast<char *>(q);
+    }
+    c->connected = true;
+    return 0;
+}
+
+__attribute__((visibility("default"))) int g8_mg_comm_barrier(g8_mg_comm *comm, void *stream) {
+    MgComm *c = reinterpret_cast<MgComm *>(comm);
+    if (!c || !c->connected) return G8_STATUS_INVALID_VALUE;
+    return comm_barrier(*c, static_cast<cudaStream_t>(stream));
+}
+
+__attribute__((visibility("default"))) int g8_mg_comm_status(g8_mg_comm *comm) {
+    MgComm *c = reinterpret_cast<MgComm *>(comm);
+    if (!c) return G8_STATUS_INVALID_VALUE;
+    uint32_t err = 0;
+    if (cudaMemcpy(&err, c->local + G8_MAX_PEERS * MG_FLAG_STRIDE, sizeof(err), cudaMemcpyDeviceToHost) != cudaSuccess) return (int)cudaGetLastError();
+    return err ? (int)cudaErrorTimeout : 0;
+}
+
+__attribute__((visibility("default"))) int g8_mg_comm_destroy(g8_mg_comm *comm) {
+    MgComm *c = reinterpret_cast<MgComm *>(comm);
+    if (!c) return 0;
+    cudaDeviceSynchronize();
+    for (int o = 0; o < c->world; ++o)
+        if (o != c->rank && c->peer[o]) cudaIpcCloseMemHandle(c->peer[o]);
+    if (c->local) cudaFree(c->local);
+    delete c;
+    return 0;
+}
+
+__attribute__((visibility("default"))) int g8_mg_plan_create(g8_mg_plan **plan, g8_mg_comm *comm, int dtype, int op_A, int op_B, size_t m, size_t n, size_t k_local,
+                                                              unsigned num_moduli, int fastmode) {
+    MgPlan *p = nullptr;
+    const int e = plan_create(&p, reinterpret_cast<MgComm *>(comm), dtype, op_A, op_B, m, n, k_local, num_moduli, fastmode != 0);
+    if (e == 0) *plan = reinterpret_cast<g8_mg_plan *>(p);
+    return e;
+}
+
+__attribute__((visibility("default"))) int g8_gemm_mg(g8_mg_plan *plan, const void *alpha, const void *A_local, size_t lda, const void *B_local, size_t ldb,
+                                                       const void *beta, void *C_slab, size_t ldc, void *stream) {
+    if (!plan) return G8_STATUS_INVALID_VALUE;
+    return run(*reinterpret_cast<MgPlan *>(plan), alpha, A_local, lda, B_local, ldb, beta, C_slab, ldc, static_cast<cudaStream_t>(stream));
+}
+
+__attribute__((visibility("default"))) int g8_mg_plan_destroy(g8_mg_plan *plan) {
+    MgPlan *p = reinterpret_cast<MgPlan *>(plan);
+    if (!p) return 0;
+    cudaDeviceSynchronize();
+    if (p->comm && p->comm->connected) { // nobody may still have our receive area mapped / in use when it is freed
+        comm_barrier(*p->comm, nullptr);
+        cudaDeviceSynchronize();
+    }
+    plan_free(p);
+    return 0;
+}
+
+} // extern "C"

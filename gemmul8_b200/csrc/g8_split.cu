@@ -19,9 +19,10 @@
 // same shuffle tree.
 #include "g8_internal.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
-#include <set>
+#include <map>
 #include <utility>
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
@@ -482,23 +483,13 @@ template <typename T> __device__ __forceinline__ T ldg_conj(const T *p, bool con
     return v;
 }
 
-// CACHE: the statistics pass (MODE 1 / 2) parks the row in shared memory so that the operand is read from HBM ONCE; element l lives
-// in 16-byte chunk c = l * sizeof(T) / 16 at physical chunk c ^ ((c >> 3) & 7), which keeps both the element-strided writes of the
-// statistics pass and the 8-consecutive-element reads of the split pass bank-conflict free for all four element types.
-template <typename T> __device__ __forceinline__ int cache_slot(int l) {
-    constexpr int PER = 16 / (int)sizeof(T) > 0 ? 16 / (int)sizeof(T) : 1; // elements per 16-byte chunk (1 for double2)
-    const int c = l / PER;
-    return (c ^ ((c >> 3) & 7)) * PER + (l - c * PER);
-}
-template <typename T, bool LARGE, int MODE, int BE, bool CACHE = false>
+template <typename T, bool LARGE, int MODE, int BE>
 __global__ void __launch_bounds__(256) split_rowcontig_kernel(SplitArgs a) {
     using U       = typename Scalar<T>::U;
     const T *in   = reinterpret_cast<const T *>(a.X) + (size_t)blockIdx.x * a.ld;
     const int row = blockIdx.x;
     const int k   = (int)a.inner;
     __shared__ U s_max[32], s_sum[32];
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *cache = reinterpret_cast<T *>(smem_raw); // [k_pad] when CACHE
     int sft;
 
     if constexpr (MODE == 0) {
@@ -511,7 +502,6 @@ __global__ void __launch_bounds__(256) split_rowcontig_kernel(SplitArgs a) {
 #pragma unroll 4
         for (int l = threadIdx.x; l < k; l += 256) {
             const T v = __ldg(in + l);
-            if constexpr (CACHE) cache[cache_slot<T>(l)] = v;
             if constexpr (MODE == 1) acc_stats<T>(v, amax, sum);
             else acc_amax<T>(v, amax);
         }
@@ -546,24 +536,17 @@ __global__ void __launch_bounds__(256) split_rowcontig_kernel(SplitArgs a) {
         }
     }
 
-    // 8 consecutive inner indices per thread -> one 64-bit store per plane, 256 B per warp
+    // 8 consecutive inner indices per thread -> one 64-bit store per plane, 256 B per warp.  (The second read of the row -- after the
+    // statistics pass of modes 1 / 2 -- mostly hits L2; parking the row in shared memory instead was measured SLOWER, r02d sweep:
+    // the 64 KB per block cut the occupancy to three blocks per SM.)
     constexpr int NV     = 8;
     const size_t row_off = (size_t)row * a.k_pad;
     for (int l = threadIdx.x * NV; l < (int)a.k_pad; l += 256 * NV) {
         T v[NV];
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            if (l + j < k) {
-                if constexpr (CACHE && (MODE == 1 || MODE == 2)) {
-                    v[j] = cache[cache_slot<T>(l + j)]; // l % 8 == 0: the 8 elements are whole, consecutive (swizzled) 16-byte chunks
-                    if constexpr (Scalar<T>::cplx)
-                        if (a.conj) v[j].y = -v[j].y;
-                } else {
-                    v[j] = ldg_conj(in + l + j, a.conj);
-                }
-            } else {
-                v[j] = T{};
-            }
+            if (l + j < k) v[j] = ldg_conj(in + l + j, a.conj);
+            else v[j] = T{};
         }
         emit_elements<T, LARGE, (MODE == 3 ? 2 : MODE), NV, BE>(v, sft, a, row_off + l);
     }
@@ -611,20 +594,33 @@ __global__ void __launch_bounds__(1024) stats_rowstrided_kernel(SplitArgs a) {
 // MODE 0: residues of trunc(x * 2^-sft); MODE 2: bound plane(s) with s0 = sft (as stored)
 // ------------------------------------------------------------------------------------------------
 constexpr int RS_TL = 128; // row-strided tile: 32 rows x 128 inner; 16 segments of 8 per row
-// load one tile (lane = row, 16 warps stride over l) into XOR-swizzled shared memory; returns nothing, caller syncs
-template <typename T> __device__ __forceinline__ void rowstrided_load_tile(const SplitArgs &a, T *tile, int r0, int l0) {
-    constexpr int SW = (sizeof(T) == 16) ? 0 : 1; // swizzle granularity that keeps both phases bank-conflict free
+// one tile = 32 rows x 128 inner; lane = row (coalesced along r), the 16 warps stride over l: every thread moves 8 elements.
+// Split into "global -> registers" and "registers -> XOR-swizzled shared memory" so that the loads of the NEXT tile can be in
+// flight while the current one is reduced (register double buffering).
+template <typename T> __device__ __forceinline__ void rowstrided_fetch_tile(const SplitArgs &a, T (&v)[RS_TL / 16], int r0, int l0) {
     const T *X     = reinterpret_cast<const T *>(a.X);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5; // 16 warps
     const int r    = r0 + lane;
 #pragma unroll
     for (int j = 0; j < RS_TL / 16; ++j) {
-        const int ll = warp + 16 * j;
-        const int l  = l0 + ll;
-        T v{};
-        if (r < (int)a.rows && l < (int)a.inner) v = ldg_conj(X + (size_t)l * a.ld + r, a.conj);
-        tile[ll * 32 + (lane ^ ((ll >> 3) << SW))] = v;
+        const int l = l0 + warp + 16 * j;
+        v[j]        = T{};
+        if (r < (int)a.rows && l < (int)a.inner) v[j] = ldg_conj(X + (size_t)l * a.ld + r, a.conj);
     }
+}
+template <typename T> __device__ __forceinline__ void rowstrided_park_tile(const T (&v)[RS_TL / 16], T *tile) {
+    constexpr int SW = (sizeof(T) == 16) ? 0 : 1; // swizzle granularity that keeps both phases bank-conflict free
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < RS_TL / 16; ++j) {
+        const int ll = warp + 16 * j;
+        tile[ll * 32 + (lane ^ ((ll >> 3) << SW))] = v[j];
+    }
+}
+template <typename T> __device__ __forceinline__ void rowstrided_load_tile(const SplitArgs &a, T *tile, int r0, int l0) {
+    T v[RS_TL / 16];
+    rowstrided_fetch_tile<T>(a, v, r0, l0);
+    rowstrided_park_tile<T>(v, tile);
 }
 // thread (rr = t / 16, seg = t % 16) owns 8 consecutive l of one row of the tile and emits one 8-byte store per plane
 template <typename T, bool LARGE, int MODE, int BE>
@@ -645,91 +641,26 @@ __device__ __forceinline__ void rowstrided_emit_tile(const SplitArgs &a, const T
     emit_elements<T, LARGE, MODE, NV, BE>(v, sft, a, off);
 }
 
+// blockIdx.y owns `tiles_per_block` consecutive tiles along l; the loads of tile t + 1 are issued before tile t is reduced.
 template <typename T, bool LARGE, int MODE, int BE>
-__global__ void __launch_bounds__(512) split_rowstrided_kernel(SplitArgs a) {
+__global__ void __launch_bounds__(512) split_rowstrided_kernel(SplitArgs a, int tiles_per_block) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *tile = reinterpret_cast<T *>(smem_raw); // [TL][32], column index XOR-swizzled by the segment number
-    const int r0 = blockIdx.x * 32, l0 = blockIdx.y * RS_TL;
-    rowstrided_load_tile<T>(a, tile, r0, l0);
-    __syncthreads();
-    const int row = r0 + (threadIdx.x >> 4);
-    if (row >= (int)a.rows) return;
-    const int sft = (MODE == 0) ? -(int)a.sft[row] : (int)a.sft[row];
-    rowstrided_emit_tile<T, LARGE, MODE, BE>(a, tile, r0, l0, sft);
-}
-
-// ------------------------------------------------------------------------------------------------
-// ROW-STRIDED accurate stage (i), fused: amax -> s0 -> bound plane(s) with ONE pass over HBM.
-// A cluster of CL CTAs owns a block of 32 rows; CTA c owns the k-slice of tiles [c * tpc, (c + 1) * tpc).  Phase A: every CTA scans
-// its slice for the per-row max |x| (order-free), the cluster combines the CL x 32 maxima through distributed shared memory.
-// Phase B: every CTA walks its slice AGAIN -- 32 rows x (k / CL) elements, e.g. 256 KB, which it has just pulled into L2 -- and emits
-// the bound plane with s0 = 5 (7) - ilogb(amax).  HBM sees the operand once; the second read is an L2 hit.
-// (Fast mode cannot use this: its round-up sum of squares has a contractual order over ALL of k per (row, l mod 32) class.)
-// ------------------------------------------------------------------------------------------------
-template <typename T, int BE, int CL>
-__global__ void __launch_bounds__(512) accu_stage1_rowstrided_kernel(SplitArgs a, int tiles_per_cta) {
-    using U = typename Scalar<T>::U;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *tile = reinterpret_cast<T *>(smem_raw);
-    __shared__ U s_part[16][33];
-    __shared__ U s_rowmax[32]; // this CTA's maxima, read by the whole cluster
-    __shared__ int s_s0[32];
     const int r0 = blockIdx.x * 32;
-    const int crank = blockIdx.y; // cluster dims (1, CL, 1): rank == blockIdx.y
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ntiles = (int)(a.k_pad / RS_TL);
-    const int t_begin = crank * tiles_per_cta, t_end = min(ntiles, t_begin + tiles_per_cta);
-
-    // ---- phase A: max |x| of row r0 + lane over this CTA's k-slice ----
-    {
-        const T *X  = reinterpret_cast<const T *>(a.X);
-        const int r = r0 + lane;
-        U amax = 0;
-        if (r < (int)a.rows) {
-            const int l_end = min((int)a.inner, t_end * RS_TL);
-#pragma unroll 8
-            for (int l = t_begin * RS_TL + warp; l < l_end; l += 16) acc_amax<T>(__ldg(X + (size_t)l * a.ld + r), amax);
-        }
-        s_part[warp][lane] = amax;
-        __syncthreads();
-        if (warp == 0) {
-            U m = s_part[0][lane];
-#pragma unroll
-            for (int w = 1; w < 16; ++w) m = max(m, s_part[w][lane]);
-            s_rowmax[lane] = m;
-        }
-    }
-    // every CTA's s_rowmax is complete and visible cluster-wide after this barrier
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-    if (warp == 0) {
-        U m = 0;
-        const uint32_t local = (uint32_t)__cvta_generic_to_shared(&s_rowmax[lane]);
-#pragma unroll
-        for (int c = 0; c < CL; ++c) {
-            uint32_t remote;
-            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(c));
-            U v;
-            if constexpr (sizeof(U) == 8) asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote));
-            else asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote));
-            m = max(m, v);
-        }
-        const int s0 = accu_s0(m) + (BE == FP8 ? 2 : 0);
-        s_s0[lane]   = s0;
-        if (crank == 0 && r0 + lane < (int)a.rows) a.sft[r0 + lane] = (int16_t)s0;
-    }
-    // remote reads of s_rowmax are done once every CTA has arrived here; nobody exits (or reuses smem) before the matching wait below
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    __syncthreads();
-
-    // ---- phase B: bound plane(s) of the same slice (L2 hits) ----
-    const int s0 = s_s0[threadIdx.x >> 4];
+    const int t_begin = blockIdx.y * tiles_per_block, t_end = min(ntiles, t_begin + tiles_per_block);
+    const int row = r0 + (threadIdx.x >> 4);
+    int sft = 0;
+    if (row < (int)a.rows) sft = (MODE == 0) ? -(int)a.sft[row] : (int)a.sft[row];
+    T v[RS_TL / 16];
+    rowstrided_fetch_tile<T>(a, v, r0, t_begin * RS_TL);
     for (int t = t_begin; t < t_end; ++t) {
-        rowstrided_load_tile<T>(a, tile, r0, t * RS_TL);
+        rowstrided_park_tile<T>(v, tile);
         __syncthreads();
-        rowstrided_emit_tile<T, false, 2, BE>(a, tile, r0, t * RS_TL, s0);
+        if (t + 1 < t_end) rowstrided_fetch_tile<T>(a, v, r0, (t + 1) * RS_TL); // in flight during the reduction below
+        rowstrided_emit_tile<T, LARGE, MODE, BE>(a, tile, r0, t * RS_TL, sft);
         __syncthreads();
     }
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // accurate mode, stage (iii): sft = -(s0 + floor(fmaf_rd(-0x1.000006p-1f, log2f(float(max)), log2P)))
@@ -751,15 +682,17 @@ __global__ void finalize_accu_shift_kernel(int16_t *__restrict__ sft, const int3
 // |x| can exceed 2^63 (two level-1 folds needed) once num_moduli passes the backend's M threshold (common.hpp:15-27)
 static bool is_large(int backend, int num_moduli) { return num_moduli > thresholds(backend).M; }
 
-// dynamic shared memory beyond 48 KB needs a one-time opt-in per kernel AND per device (never repeated on the launch path)
+// dynamic shared memory beyond 48 KB needs an opt-in per kernel AND per device: done once per (kernel, device, size high-water mark),
+// never repeated on the launch path.  The attribute is set to exactly what is requested (static + dynamic must stay <= 227 KB).
 static void ensure_smem(const void *kern, size_t smem) {
     if (smem <= 48 * 1024) return;
     static std::mutex mu;
-    static std::set<std::pair<const void *, int>> done;
+    static std::map<std::pair<const void *, int>, size_t> granted;
     int dev = 0;
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lock(mu);
-    if (done.insert({kern, dev}).second) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    size_t &have = granted[{kern, dev}];
+    if (smem > have && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) have = smem;
 }
 static int env_flag(const char *name, int dflt) {
     const char *e = getenv(name);
@@ -768,48 +701,25 @@ static int env_flag(const char *name, int dflt) {
 
 template <typename T, int MODE, int BE> static void launch_rowcontig(const SplitArgs &a, bool large, cudaStream_t st) {
     const dim3 grid((unsigned)a.rows);
-    // statistics modes: park the row in shared memory when it fits (<= 64 KB: three blocks per SM) so that HBM is read once
-    static const int cache_pref = env_flag("G8_SPLIT_ROW_CACHE", 1);
-    const size_t row_bytes = a.k_pad * sizeof(T);
-    auto go = [&](auto plain, auto cached) {
-        if ((MODE == 1 || MODE == 2) && cache_pref && row_bytes <= 64 * 1024) {
-            ensure_smem(reinterpret_cast<const void *>(cached), row_bytes);
-            cached<<<grid, 256, row_bytes, st>>>(a);
-        } else {
-            plain<<<grid, 256, 0, st>>>(a);
-        }
-    };
-    if (MODE >= 2 || !large) go(split_rowcontig_kernel<T, false, MODE, BE, false>, split_rowcontig_kernel<T, false, MODE, BE, true>);
-    else go(split_rowcontig_kernel<T, true, MODE, BE, false>, split_rowcontig_kernel<T, true, MODE, BE, true>);
+    if (MODE >= 2 || !large) split_rowcontig_kernel<T, false, MODE, BE><<<grid, 256, 0, st>>>(a);
+    else split_rowcontig_kernel<T, true, MODE, BE><<<grid, 256, 0, st>>>(a);
 }
 
 template <typename T, int MODE, int BE> static void launch_rowstrided(const SplitArgs &a, bool large, cudaStream_t st) {
-    const dim3 grid((unsigned)((a.rows + 31) / 32), (unsigned)(a.k_pad / RS_TL));
+    // several tiles per block (software-pipelined), but still >= ~8 blocks per SM for load balance
+    static const int tpb_pref = env_flag("G8_SPLIT_TILES_PER_BLOCK", 4);
+    const int ntiles = (int)(a.k_pad / RS_TL);
+    const size_t row_blocks = (a.rows + 31) / 32;
+    int tpb = std::max(1, std::min(tpb_pref, ntiles));
+    while (tpb > 1 && row_blocks * ((ntiles + tpb - 1) / tpb) < 1200) tpb >>= 1;
+    const dim3 grid((unsigned)row_blocks, (unsigned)((ntiles + tpb - 1) / tpb));
     const size_t smem = RS_TL * 32 * sizeof(T);
     auto go = [&](auto kern) {
         ensure_smem(reinterpret_cast<const void *>(kern), smem);
-        kern<<<grid, 512, smem, st>>>(a);
+        kern<<<grid, 512, smem, st>>>(a, tpb);
     };
     if (MODE == 2 || !large) go(split_rowstrided_kernel<T, false, MODE, BE>);
     else go(split_rowstrided_kernel<T, true, MODE, BE>);
-}
-
-// accurate stage (i) for a row-strided operand in ONE launch (cluster of 8 CTAs per 32-row block), see accu_stage1_rowstrided_kernel
-template <typename T, int BE> static bool launch_accu_stage1_rowstrided(const SplitArgs &a, cudaStream_t st) {
-    constexpr int CL = 8;
-    static const int pref = env_flag("G8_SPLIT_FUSED_ACCU", 1);
-    const int ntiles = (int)(a.k_pad / RS_TL);
-    if (!pref || ntiles < CL) return false; // short k: the two-kernel path is just as good
-    const size_t smem = RS_TL * 32 * sizeof(T);
-    auto kern = accu_stage1_rowstrided_kernel<T, BE, CL>;
-    ensure_smem(reinterpret_cast<const void *>(kern), smem);
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)((a.rows + 31) / 32), CL), cfg.blockDim = dim3(512), cfg.dynamicSmemBytes = smem, cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1, attr[0].val.clusterDim.y = CL, attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, a, (ntiles + CL - 1) / CL) == cudaSuccess;
 }
 
 template <typename T, int BE> static void split_typed(const SplitArgs &a, int mode, cudaStream_t st) {
@@ -821,7 +731,6 @@ template <typename T, int BE> static void split_typed(const SplitArgs &a, int mo
         else launch_rowcontig<T, 3, BE>(a, large, st);
     } else {
         const dim3 sgrid((unsigned)((a.rows + 31) / 32)), sblock(32, 32);
-        if (mode == 2 && launch_accu_stage1_rowstrided<T, BE>(a, st)) return;
         if (mode == 1) stats_rowstrided_kernel<T, 1, BE><<<sgrid, sblock, 0, st>>>(a);
         if (mode == 2) stats_rowstrided_kernel<T, 2, BE><<<sgrid, sblock, 0, st>>>(a);
         if (mode >= 2) launch_rowstrided<T, 2, BE>(a, large, st);

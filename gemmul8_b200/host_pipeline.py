@@ -187,10 +187,52 @@ class HostGemm:
         return done
 
 
+class NativeHostGemm:
+    """The NATIVE host-buffer pipeline (C ABI g8_host_plan_create / g8_gemm_host / g8_host_plan_destroy, csrc/g8_host.cu): the same
+    chunked three-stream schedule as HostGemm above, driven entirely from C++, for all four types, both backends and every
+    op_A / op_B.  This class only holds the opaque plan; `run` enqueues one call on torch's current stream (stream-ordered, does not
+    block the host) -- what bench.py's `e2e` leg measures."""
+
+    def __init__(self, m, n, k, dtype=torch.float64, num_moduli=14, fastmode=False, op_A="N", op_B="N", chunk=1024, device=None, backend=0):
+        self.lib = _lib.load()
+        self.dtype = dtype
+        self.dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.plan = ctypes.c_void_p()
+        with torch.cuda.device(self.dev):
+            api._check(self.lib.g8_host_plan_create(ctypes.byref(self.plan), api._DTYPES[dtype], int(backend), api._op(op_A), api._op(op_B), m, n, k,
+                                                    num_moduli, int(bool(fastmode)), chunk), "g8_host_plan_create")
+        rowsA = m if api._op(op_A) == 0 else k
+        self.defaults = (rowsA, k if api._op(op_B) == 0 else n, m)
+
+    def run(self, hA, hB, hC, alpha=1.0, beta=0.0, lda=None, ldb=None, ldc=None):
+        keep = []
+        pa, pb = api._scalar_ptr(alpha, self.dtype, keep), api._scalar_ptr(beta, self.dtype, keep)
+        with torch.cuda.device(self.dev):
+            api._check(self.lib.g8_gemm_host(self.plan, pa, hA.data_ptr(), lda or self.defaults[0], hB.data_ptr(), ldb or self.defaults[1], pb,
+                                             hC.data_ptr(), ldc or self.defaults[2], torch.cuda.current_stream(self.dev).cuda_stream), "g8_gemm_host")
+
+    def close(self):
+        if self.plan:
+            self.lib.g8_host_plan_destroy(self.plan)
+            self.plan = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def gemm_host(op_A, op_B, m, n, k, alpha, hA, lda, hB, ldb, beta, hC, ldc, num_moduli=14, fastmode=False, chunk=1024, device=None,
-              plan=None):
-    """One-shot convenience around HostGemm (pass `plan=` to reuse the device buffers across calls). Synchronises."""
-    plan = plan or HostGemm(m, n, k, hC.dtype, num_moduli, fastmode, op_A, op_B, chunk, device)
+              plan=None, backend=0, native=True):
+    """One-shot convenience (pass `plan=` to reuse the device buffers across calls).  Synchronises.  native=True (default) runs the
+    C++ pipeline (g8_gemm_host); native=False the Python-orchestrated one (INT8 backend only)."""
+    if plan is None:
+        plan = (NativeHostGemm(m, n, k, hC.dtype, num_moduli, fastmode, op_A, op_B, chunk, device, backend) if native else
+                HostGemm(m, n, k, hC.dtype, num_moduli, fastmode, op_A, op_B, chunk, device))
     ev = plan.run(hA, hB, hC, alpha, beta, lda, ldb, ldc)
-    ev.synchronize()
+    if ev is not None:
+        ev.synchronize()
+    else:
+        torch.cuda.current_stream(plan.dev).synchronize()
     return plan

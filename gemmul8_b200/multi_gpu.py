@@ -393,6 +393,61 @@ class KShardGemm:
         return C
 
 
+class NativeKShardGemm:
+    """K-sharded emulated GEMM driven ENTIRELY by the native library (C ABI g8_mg_comm_* / g8_mg_plan_* / g8_gemm_mg, csrc/g8_mg.cu):
+    orchestration in C++, every inter-rank exchange through the library's own kernels over NVLink peer memory (fused GEMM -> scatter,
+    mailbox all-reduce in fixed rank order, flag barrier) -- no NCCL on the path.  torch.distributed is used ONCE, at construction, to
+    pass the 64-byte IPC handles around (any transport would do; tests/native/mg_check.cu uses a shared mapping and no Python at all).
+    Same interface as KShardGemm."""
+
+    def __init__(self, m, n, k_local, num_moduli, fastmode=False, dtype=torch.float64, device=None, group=None, op_A="N", op_B="N"):
+        from . import _lib
+        if dtype not in (torch.float32, torch.float64):
+            raise NotImplementedError("K-sharded path: real S/D GEMM only")
+        self.lib, self.group = _lib.load(), group
+        self.W, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.m, self.n, self.k, self.N, self.dtype = m, n, k_local, num_moduli, dtype
+        self.dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.opA, self.opB = api._op(op_A), api._op(op_B)
+        self.nc = n // self.W
+        self.local_out_elems = m * self.nc
+        self.comm, self.plan = ctypes.c_void_p(), ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        vec = max(8 * (m + n), 4 * (pad256(m) + pad256(n)))
+        with torch.cuda.device(self.dev):
+            api._check(self.lib.g8_mg_comm_create(ctypes.byref(self.comm), self.W, self.rank, vec, handle), "g8_mg_comm_create")
+            handles = [None] * self.W
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            api._check(self.lib.g8_mg_comm_connect(self.comm, ctypes.create_string_buffer(b"".join(handles), 64 * self.W)), "g8_mg_comm_connect")
+            dist.barrier(group=group)
+            api._check(self.lib.g8_mg_plan_create(ctypes.byref(self.plan), self.comm, api._DTYPES[dtype], self.opA, self.opB, m, n, k_local,
+                                                  num_moduli, int(bool(fastmode))), "g8_mg_plan_create")
+        self.lda = m if self.opA == 0 else k_local
+        self.ldb = k_local if self.opB == 0 else n
+
+    def local_out(self, C):
+        return C[:self.local_out_elems]
+
+    def trace_report(self):
+        return []
+
+    def run(self, A, B, C, alpha=1.0, beta=0.0):
+        keep = []
+        pa, pb = api._scalar_ptr(alpha, self.dtype, keep), api._scalar_ptr(beta, self.dtype, keep)
+        with torch.cuda.device(self.dev):
+            api._check(self.lib.g8_gemm_mg(self.plan, pa, A.data_ptr(), self.lda, B.data_ptr(), self.ldb, pb, C.data_ptr(), self.m,
+                                           torch.cuda.current_stream(self.dev).cuda_stream), "g8_gemm_mg")
+        return C
+
+    def close(self):
+        if self.plan:
+            with torch.cuda.device(self.dev):
+                self.lib.g8_mg_plan_destroy(self.plan)
+                dist.barrier(group=self.group)
+                self.lib.g8_mg_comm_destroy(self.comm)
+            self.plan, self.comm = ctypes.c_void_p(), ctypes.c_void_p()
+
+
 class ModShardGemm:
     """Modulus-set sharded multi-GPU emulated GEMM (SURVEY section 8e "modulus-set shard"): every rank holds ALL of A and B, computes
     the shifts and the residue planes redundantly (no communication, bit-identical on every rank by construction), contracts only ITS
@@ -517,7 +572,8 @@ def verify_against_single_gpu(shard, world, rank, dev, num_moduli, fastmode, var
     seedA = lambda r: 777 + (1000 * r if shard == "k" else 0)
     seedB = lambda r: 999 + (1000 * r if shard in ("k", "n") else 0)
     if shard == "k":
-        g = KShardGemm(m, n, k_local, num_moduli, fastmode=fastmode, dtype=dt, device=dev, variant=variant)
+        g = (NativeKShardGemm(m, n, k_local, num_moduli, fastmode=fastmode, dtype=dt, device=dev) if variant == "native" else
+             KShardGemm(m, n, k_local, num_moduli, fastmode=fastmode, dtype=dt, device=dev, variant=variant))
         k_tot = k_local * world
         A_full = torch.cat([g8api.randmat(m, k_local, dt, phi=0.5, seed=seedA(r), device=dev) for r in range(world)])
         B_full = torch.cat([g8api.randmat(k_local, n, dt, phi=0.5, seed=seedB(r), device=dev).view(n, k_local) for r in range(world)], dim=1).contiguous().view(-1)

@@ -145,6 +145,53 @@ int g8_stage_stats(int dtype, int is_A, int op, size_t rows, size_t k, const voi
  * kind 1 = accurate-mode first shift s0 = 5 - ilogb(amax) (src/scaling_accu_real.hpp:39) */
 int g8_stage_shift_from_stats(const double *amax, const double *sumsq, size_t count, unsigned num_moduli, int kind, int16_t *sft, void *stream);
 
+/* ---- emulated GEMM on HOST buffers (new work; the reference's API takes device pointers only, include/gemmul8.hpp:41-94) ----
+ * A plan owns the device buffers (residue planes, C_mid, staging chunks) and three streams for one problem shape; it is re-usable
+ * across calls.  g8_gemm_host copies A, streams op(B) in chunks of `chunk_cols` columns (0 = 1024; rounded to 256) while the stage
+ * kernels of the previous chunk run, and streams C back the same way.  hA / hB / hC are HOST pointers (pinned memory lets the copies
+ * overlap; pageable memory works, slower), column-major with leading dimensions lda / ldb / ldc exactly as in g8_gemm; alpha / beta
+ * are HOST scalars.  Work is ordered after everything already enqueued on `stream`, and `stream` continues after the last byte of C
+ * has arrived -- the call itself does not block.  The result is bit-identical to g8_gemm on device copies of the same matrices.
+ * All four types, both backends, all op_A / op_B combinations. */
+typedef struct g8_host_plan g8_host_plan;
+int g8_host_plan_create(g8_host_plan **plan, int dtype, int backend, int op_A, int op_B, size_t m, size_t n, size_t k, unsigned num_moduli,
+                        int fastmode, size_t chunk_cols);
+int g8_gemm_host(g8_host_plan *plan, const void *alpha, const void *hA, size_t lda, const void *hB, size_t ldb, const void *beta, void *hC,
+                 size_t ldc, void *stream);
+int g8_host_plan_destroy(g8_host_plan *plan);
+
+/* ---- native K-sharded multi-GPU emulated GEMM (new work; the reference is single-GPU) ----
+ * One process per GPU of one NVLink / NVSwitch node.  Rank r owns the K-slab  op(A)[:, K_r] (m x k_local)  and  op(B)[K_r, :]
+ * (k_local x n)  and receives the column slab  C[:, r*n/world : (r+1)*n/world]  of  alpha * sum_r op(A)_r op(B)_r + beta * C.
+ * All inter-rank traffic goes through peer memory (CUDA IPC) and this library's own kernels: the GEMM epilogue scatters the residue
+ * tiles to their owners, small vectors (row statistics, bound maxima) are all-reduced through per-rank mailboxes in a fixed rank
+ * order, ranks are ordered with a flag exchange -- no NCCL / MPI on the path.  The caller only moves one 64-byte handle per rank
+ * around at start-up, with any transport it has (pipe, file, MPI, torch.distributed ...).
+ *
+ *   g8_mg_comm_create   allocates this rank's mailbox (sized for vectors of `max_vector_bytes`: at least 8 * (m + n) for the largest
+ *                       problem) and returns its IPC handle in handle64;
+ *   g8_mg_comm_connect  takes the world x 64 bytes of all ranks' handles in rank order (its own entry is ignored);
+ *   g8_mg_plan_create   COLLECTIVE: allocates the planes and the peer-mapped receive area of one problem shape and exchanges the
+ *                       receive-area handles through the communicator.  dtype G8_R32F / G8_R64F, INT8 backend, any op_A / op_B;
+ *                       n / world must be a multiple of 256, world * k_local <= 2^17;
+ *   g8_gemm_mg          COLLECTIVE, asynchronous on `stream`: every rank passes its slabs (device pointers, column-major, leading
+ *                       dimensions lda / ldb) and gets its m x (n / world) slab of C (ld ldc); alpha / beta as in g8_gemm;
+ *   g8_mg_comm_barrier  stream-ordered barrier across the ranks;  g8_mg_comm_status  != 0 after a peer timed out (~20 s).
+ * Accurate mode is bit-identical to g8_gemm on the concatenated operands; fast mode is identical on all ranks and equal to the
+ * single-GPU result except where the differently ordered sum of squares moves a shift across a floor() boundary. */
+typedef struct g8_mg_comm g8_mg_comm;
+typedef struct g8_mg_plan g8_mg_plan;
+int g8_mg_comm_create(g8_mg_comm **comm, int world, int rank, size_t max_vector_bytes, void *handle64);
+int g8_mg_comm_connect(g8_mg_comm *comm, const void *handles /* world x 64 bytes, rank order */);
+int g8_mg_comm_barrier(g8_mg_comm *comm, void *stream);
+int g8_mg_comm_status(g8_mg_comm *comm);
+int g8_mg_comm_destroy(g8_mg_comm *comm);
+int g8_mg_plan_create(g8_mg_plan **plan, g8_mg_comm *comm, int dtype, int op_A, int op_B, size_t m, size_t n, size_t k_local, unsigned num_moduli,
+                      int fastmode);
+int g8_gemm_mg(g8_mg_plan *plan, const void *alpha, const void *A_local, size_t lda, const void *B_local, size_t ldb, const void *beta,
+               void *C_slab, size_t ldc, void *stream);
+int g8_mg_plan_destroy(g8_mg_plan *plan);
+
 /* Synthetic test matrices with the reference harness' generator (testing/make_matrix.hpp:33-82):
  * element idx <- curand_init(seed, idx, 0); phi < 0: standard normal, else (u-0.5)*exp(g*phi). */
 int g8_randmat(int dtype, void *X, size_t rows, size_t cols, double phi, unsigned long long seed, void *stream);

@@ -1,17 +1,26 @@
-// Restated from the reference's debug/test_hijack.cu: plain cuBLAS calls; run once natively and once under
-// LD_PRELOAD=libgemmul8.so with GEMMUL8_* set; prints a checksum line per call so the harness can compare both runs.
+// Restated from the reference's debug/test_hijack.cu: plain cuBLAS calls; run natively, under LD_PRELOAD=<this repo's libgemmul8.so>
+// and under LD_PRELOAD=<the reference's own hook library> with GEMMUL8_* set; prints a checksum line per call so the harness can
+// compare the runs (emulated vs native by tolerance, this repo vs the reference hook EXACTLY).
 // With GEMMUL8_SKIP_SCALE_{A,B}=1 the same A/B are reused across calls and then replaced, to exercise cache invalidation
-// (debug/test_hijack.cu:164-177).
+// (debug/test_hijack.cu:164-177).  Also covered: cublasCgemm / cublasZgemm, complex cublasGemmEx, a stream switch on one handle
+// (hook.cu:141-162) and two host threads sharing one handle (hook.cu:126-134,633-634).
 #include <cublas_v2.h>
+#include <cuComplex.h>
 #include <cuda_runtime.h>
 #include <cmath>
 #include <cstdio>
 #include <random>
+#include <thread>
 #include <vector>
 static double checksum(const std::vector<double> &v) {
     double s = 0;
     for (size_t i = 0; i < v.size(); ++i) s += v[i] * (1.0 + (i % 7));
     return s;
+}
+template <typename T> static std::vector<double> as_doubles(const T *d, size_t count) { // count = number of real scalars
+    std::vector<T> h(count);
+    cudaMemcpy(h.data(), d, sizeof(T) * count, cudaMemcpyDeviceToHost);
+    return std::vector<double>(h.begin(), h.end());
 }
 int main() {
     std::mt19937 rng(9999);
@@ -35,12 +44,10 @@ int main() {
         }
         cudaMemset(C, 0, sizeof(double) * 128 * 128);
         cublasDgemm(h, CUBLAS_OP_N, it == 2 ? CUBLAS_OP_T : CUBLAS_OP_N, m, n, k, it == 1 ? &half : &one, A, 128, B, 128, &zero, C, 128);
-        std::vector<double> hC(128 * 128);
-        cudaMemcpy(hC.data(), C, sizeof(double) * hC.size(), cudaMemcpyDeviceToHost);
-        std::printf("dgemm %d %dx%dx%d checksum %.17g\n", it, m, n, k, checksum(hC));
+        std::printf("dgemm %d %dx%dx%d checksum %.17g\n", it, m, n, k, checksum(as_doubles(C, 128 * 128)));
     }
     // float path
-    std::vector<float> fA(64 * 64), fB(64 * 64), fC(64 * 64);
+    std::vector<float> fA(64 * 64), fB(64 * 64);
     for (auto &x : fA) x = (float)nd(rng);
     for (auto &x : fB) x = (float)nd(rng);
     float *dA, *dB, *dC;
@@ -48,15 +55,66 @@ int main() {
     cudaMemcpy(dA, fA.data(), 4 * 64 * 64, cudaMemcpyHostToDevice), cudaMemcpy(dB, fB.data(), 4 * 64 * 64, cudaMemcpyHostToDevice);
     const float fone = 1.f, fzero = 0.f;
     cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, 64, 64, 64, &fone, dA, 64, dB, 64, &fzero, dC, 64);
-    cudaMemcpy(fC.data(), dC, 4 * 64 * 64, cudaMemcpyDeviceToHost);
-    double s = 0;
-    for (size_t i = 0; i < fC.size(); ++i) s += fC[i] * (1.0 + (i % 7));
-    std::printf("sgemm 64 checksum %.9g\n", s);
+    std::printf("sgemm 64 checksum %.9g\n", checksum(as_doubles(dC, 64 * 64)));
     cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, 64, 48, 80, &one, A, CUDA_R_64F, 128, B, CUDA_R_64F, 128, &zero, C, CUDA_R_64F, 128,
                  CUBLAS_COMPUTE_64F, CUBLAS_GEMM_DEFAULT);
-    std::vector<double> hC(128 * 128);
-    cudaMemcpy(hC.data(), C, sizeof(double) * hC.size(), cudaMemcpyDeviceToHost);
-    std::printf("gemmex 64x48x80 checksum %.17g\n", checksum(hC));
+    std::printf("gemmex 64x48x80 checksum %.17g\n", checksum(as_doubles(C, 128 * 128)));
+
+    // ---- complex: the 128 x 128 double buffers reinterpreted as 64 x 128 cuDoubleComplex (ld 64), the float ones as 32 x 64 cuComplex ----
+    {
+        const cuDoubleComplex zal = make_cuDoubleComplex(0.75, -0.5), zbe = make_cuDoubleComplex(0.0, 0.0);
+        auto *zA = reinterpret_cast<cuDoubleComplex *>(A), *zB = reinterpret_cast<cuDoubleComplex *>(B), *zC = reinterpret_cast<cuDoubleComplex *>(C);
+        cudaMemset(C, 0, sizeof(double) * 128 * 128);
+        cublasZgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, 40, 36, 50, &zal, zA, 64, zB, 64, &zbe, zC, 64);
+        std::printf("zgemm NN 40x36x50 checksum %.17g\n", checksum(as_doubles(C, 128 * 128)));
+        cublasZgemm(h, CUBLAS_OP_C, CUBLAS_OP_T, 40, 36, 50, &zal, zA, 64, zB, 64, &zbe, zC, 64);
+        std::printf("zgemm CT 40x36x50 checksum %.17g\n", checksum(as_doubles(C, 128 * 128)));
+        cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_C, 40, 36, 50, &zal, zA, CUDA_C_64F, 64, zB, CUDA_C_64F, 64, &zbe, zC, CUDA_C_64F, 64, CUBLAS_COMPUTE_64F,
+                     CUBLAS_GEMM_DEFAULT);
+        std::printf("zgemmex NC 40x36x50 checksum %.17g\n", checksum(as_doubles(C, 128 * 128)));
+        const cuComplex cal = make_cuComplex(1.f, 0.f), cbe = make_cuComplex(0.f, 0.f);
+        auto *cA = reinterpret_cast<cuComplex *>(dA), *cB = reinterpret_cast<cuComplex *>(dB), *cC = reinterpret_cast<cuComplex *>(dC);
+        cudaMemset(dC, 0, 4 * 64 * 64);
+        cublasCgemm(h, CUBLAS_OP_N, CUBLAS_OP_C, 30, 28, 32, &cal, cA, 32, cB, 32, &cbe, cC, 32);
+        std::printf("cgemm NC 30x28x32 checksum %.9g\n", checksum(as_doubles(dC, 64 * 64)));
+    }
+    // ---- one handle, two streams: the second call reads what the first wrote (C -> A role), ordered only by the handle's stream switch ----
+    {
+        cudaStream_t s1, s2;
+        cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking), cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+        double *T1, *T2;
+        cudaMalloc(&T1, sizeof(double) * 128 * 128), cudaMalloc(&T2, sizeof(double) * 128 * 128);
+        cudaMemset(T1, 0, sizeof(double) * 128 * 128), cudaMemset(T2, 0, sizeof(double) * 128 * 128);
+        cudaDeviceSynchronize();
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cublasSetStream(h, s1);
+        cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, 64, 64, 64, &one, A, 128, B, 128, &zero, T1, 128);
+        cudaEventRecord(ev, s1);
+        cudaStreamWaitEvent(s2, ev, 0); // the application orders its own data dependency; the hook must order its shared workspaces
+        cublasSetStream(h, s2);
+        cublasDgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, 64, 64, 64, &one, T1, 128, B, 128, &zero, T2, 128);
+        cudaStreamSynchronize(s2);
+        std::printf("streams chained checksum %.17g\n", checksum(as_doubles(T2, 128 * 128)));
+        cublasSetStream(h, nullptr);
+        cudaFree(T1), cudaFree(T2);
+    }
+    // ---- two host threads on ONE handle (default stream), each with its own output ----
+    {
+        double *T[2];
+        for (auto &p : T) cudaMalloc(&p, sizeof(double) * 128 * 128), cudaMemset(p, 0, sizeof(double) * 128 * 128);
+        cudaDeviceSynchronize();
+        auto work = [&](int id) {
+            for (int r = 0; r < 4; ++r)
+                cublasDgemm(h, id ? CUBLAS_OP_T : CUBLAS_OP_N, CUBLAS_OP_N, 64, 48, 64, &one, A, 128, B, 128, r ? &one : &zero, T[id], 128);
+        };
+        std::thread t0(work, 0), t1(work, 1);
+        t0.join(), t1.join();
+        cudaDeviceSynchronize();
+        std::printf("threads 0 checksum %.17g\n", checksum(as_doubles(T[0], 128 * 128)));
+        std::printf("threads 1 checksum %.17g\n", checksum(as_doubles(T[1], 128 * 128)));
+        cudaFree(T[0]), cudaFree(T[1]);
+    }
     cublasDestroy(h);
     return 0;
 }

@@ -51,16 +51,17 @@ def _worker(rank, world, port, q):
                 tot, _, _ = g8.work_size(m, n, K, N)
                 work = torch.empty(tot, dtype=torch.uint8, device=f"cuda:{rank}")
                 g8.gemm("N", "N", m, n, K, 1.0, A, m, B, K, 0.0, Cfull, m, N, fast, work)
-                for variant in ("int32", "residue", "fused", "fused-sumpass"):
+                for variant in ("int32", "residue", "fused", "fused-sumpass", "native"):
                     # "fused-sumpass": more than 4 shards with the separate residue_sum pass instead of the 8-part CRT kernel
                     os.environ["G8_MG_SUM_IN_CRT"] = "0" if variant == "fused-sumpass" else "1"
                     if variant == "fused-sumpass":
                         if world <= 4:
                             continue
                         variant = "fused"
-                    plan = multi_gpu.KShardGemm(m, n, kl, N, fastmode=fast, dtype=dtype, device=f"cuda:{rank}", variant=variant)
+                    plan = (multi_gpu.NativeKShardGemm(m, n, kl, N, fastmode=fast, dtype=dtype, device=f"cuda:{rank}") if variant == "native" else
+                            multi_gpu.KShardGemm(m, n, kl, N, fastmode=fast, dtype=dtype, device=f"cuda:{rank}", variant=variant))
                     C = torch.zeros(plan.local_out_elems, dtype=dtype, device=f"cuda:{rank}")
-                    for _ in range(2 if variant == "fused" else 1):   # the fused variant re-uses peer-mapped receive areas across steps
+                    for _ in range(2 if variant in ("fused", "native") else 1):   # peer-mapped receive areas are re-used across steps
                         plan.run(Ar, Br, C)
                     torch.cuda.synchronize()
                     plan.close()
@@ -218,3 +219,17 @@ def test_modshard_nccl_matches_single_gpu(cuda):
     for p in procs:
         p.join(timeout=120)
     assert all(ok for _, ok in res), res
+
+
+def test_native_multi_gpu_program_without_python(cuda):
+    """tests/native/mg_check: one forked process per GPU drives g8_mg_comm_* / g8_mg_plan_* / g8_gemm_mg through the C ABI only (no
+    Python, no NCCL, handles through a shared mapping) and compares every rank's slab with the single-GPU g8_gemm bit for bit"""
+    import subprocess
+
+    if _world() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = ROOT / "tests" / "native" / "_build" / "mg_check"
+    if not exe.exists():
+        subprocess.check_call(["make", "-C", str(ROOT / "tests" / "native")])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "mg_check OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

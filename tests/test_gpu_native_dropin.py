@@ -12,6 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 NATIVE = ROOT / "tests" / "native"
 LIB = ROOT / "gemmul8_b200" / "lib" / "libgemmul8.so"
+REF_HOOK = ROOT / "oracle" / "_ref" / "libgemmul8_refhook.so"   # the reference's own lib/libgemmul8.so (gemmul8.cu + hook.cu, unmodified)
 
 
 @pytest.fixture(scope="module")
@@ -31,7 +32,7 @@ def _run_hook(binaries, env_extra, preload):
     env = dict(os.environ)
     env.update(env_extra)
     if preload:
-        env["LD_PRELOAD"] = str(LIB)
+        env["LD_PRELOAD"] = str(LIB if preload is True else preload)
     r = subprocess.run([str(binaries / "hook_check")], capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     return [(ln.split(" checksum ")[0], float(ln.split(" checksum ")[1])) for ln in r.stdout.splitlines() if " checksum " in ln], r.stderr
@@ -39,28 +40,49 @@ def _run_hook(binaries, env_extra, preload):
 
 def test_ld_preload_hook_matches_native_cublas(binaries):
     native, _ = _run_hook(binaries, {}, False)
-    assert len(native) == 6
+    assert len(native) == 13
     # not enabled (NUM_MOD unset -> 0): every call must fall through to the real cuBLAS => identical bits
     passthrough, _ = _run_hook(binaries, {}, True)
     assert passthrough == native
-    base = {"GEMMUL8_NUM_MOD_D": "15", "GEMMUL8_NUM_MOD_S": "8"}
-    for extra in ({}, {"GEMMUL8_FASTMODE_D": "1", "GEMMUL8_FASTMODE_S": "1"},
+    base = {"GEMMUL8_NUM_MOD_D": "15", "GEMMUL8_NUM_MOD_S": "8", "GEMMUL8_NUM_MOD_Z": "15", "GEMMUL8_NUM_MOD_C": "8"}
+    for extra in ({}, {"GEMMUL8_FASTMODE_D": "1", "GEMMUL8_FASTMODE_S": "1", "GEMMUL8_FASTMODE_Z": "1", "GEMMUL8_FASTMODE_C": "1"},
                   {"GEMMUL8_SKIP_SCALE_A": "1", "GEMMUL8_SKIP_SCALE_B": "1", "GEMMUL8_MAX_M": "128", "GEMMUL8_MAX_N": "128",
                    "GEMMUL8_MAX_K": "128", "GEMMUL8_MAX_NUM_MOD": "15"}):
         emu, err = _run_hook(binaries, {**base, **extra}, True)
         assert "failed" not in err, err
         assert [a for a, _ in emu] == [a for a, _ in native]
         for (name, x), (_, y) in zip(emu, native):
-            tol = 2e-5 if name.startswith("sgemm") else (1e-9 if "FASTMODE_D" in extra else 1e-11)
+            single = name.startswith("sgemm") or name.startswith("cgemm")
+            tol = 2e-5 if single else (1e-9 if "FASTMODE_D" in extra else 1e-11)
             assert abs(x - y) <= tol * max(1.0, abs(y)), (name, x, y, extra)
     # GEMMUL8_BACKEND=FP8 (hook.cu:567-584): e4m3 emulation, ~9.2 bits per modulus -> N = 13 / 6 reach the same accuracy class
-    emu, err = _run_hook(binaries, {"GEMMUL8_NUM_MOD_D": "13", "GEMMUL8_NUM_MOD_S": "6", "GEMMUL8_BACKEND": "FP8"}, True)
+    emu, err = _run_hook(binaries, {"GEMMUL8_NUM_MOD_D": "13", "GEMMUL8_NUM_MOD_S": "6", "GEMMUL8_NUM_MOD_Z": "13", "GEMMUL8_NUM_MOD_C": "6",
+                                    "GEMMUL8_BACKEND": "FP8"}, True)
     assert "failed" not in err, err
     for (name, x), (_, y) in zip(emu, native):
-        assert abs(x - y) <= (2e-5 if name.startswith("sgemm") else 1e-10) * max(1.0, abs(y)), (name, x, y, "FP8")
+        single = name.startswith("sgemm") or name.startswith("cgemm")
+        assert abs(x - y) <= (2e-5 if single else 1e-10) * max(1.0, abs(y)), (name, x, y, "FP8")
     # out-of-range moduli count -> native path again (hook.cu:625-629)
     off, _ = _run_hook(binaries, {"GEMMUL8_NUM_MOD_D": "21", "GEMMUL8_NUM_MOD_S": "14"}, True)
     assert off == native
+
+
+def test_ld_preload_hook_bit_identical_to_reference_hook(binaries):
+    """The same unmodified cuBLAS program under LD_PRELOAD of THIS repo's libgemmul8.so and of the reference's own hook library
+    (oracle/_ref/libgemmul8_refhook.so = gemmul8.cu + hook.cu compiled where they lie): every checksum -- S/D/C/ZGEMM, real and
+    complex GemmEx, the skip-scaling cache incl. its invalidation, a stream switch, two threads on one handle -- must be EQUAL."""
+    if not REF_HOOK.exists():
+        pytest.skip("oracle/_ref/libgemmul8_refhook.so not built (needs /root/reference at build time)")
+    base = {"GEMMUL8_NUM_MOD_D": "15", "GEMMUL8_NUM_MOD_S": "8", "GEMMUL8_NUM_MOD_Z": "15", "GEMMUL8_NUM_MOD_C": "8"}
+    fastm = {"GEMMUL8_FASTMODE_D": "1", "GEMMUL8_FASTMODE_S": "1", "GEMMUL8_FASTMODE_Z": "1", "GEMMUL8_FASTMODE_C": "1"}
+    skip = {"GEMMUL8_SKIP_SCALE_A": "1", "GEMMUL8_SKIP_SCALE_B": "1", "GEMMUL8_MAX_M": "128", "GEMMUL8_MAX_N": "128", "GEMMUL8_MAX_K": "128",
+            "GEMMUL8_MAX_NUM_MOD": "15"}
+    for extra in ({}, fastm, skip, {**fastm, **skip}):
+        ours, err1 = _run_hook(binaries, {**base, **extra}, True)
+        ref, err2 = _run_hook(binaries, {**base, **extra}, REF_HOOK)
+        assert "failed" not in err1, err1
+        assert len(ours) == len(ref) == 13
+        assert ours == ref, (extra, [(a, x, y) for (a, x), (_, y) in zip(ours, ref) if x != y])
 
 
 def test_exported_symbols_match_reference():

@@ -207,11 +207,51 @@ def test_host_pipeline_bitwise(env, dtype, N, fast):
         dC, _ = H.to_dev_colmajor(C0, ldc)
         hA, hB, hC = dA.cpu().pin_memory(), dB.cpu().pin_memory(), dC.cpu().pin_memory()
         sentinel = hC.clone()
-        g8.gemm_host(opA, opB, m, n, k, 1.0, hA, lda, hB, ldb, beta, hC, ldc, num_moduli=N, fastmode=fast, chunk=256)
-        got = hC.numpy().reshape(n, ldc)[:, :m].T.copy()
-        assert H.bits_equal(got, want), H.first_diff(got, want, f"C {opA}{opB}")
-        if ldc > m:  # padding rows of the caller's buffer must be untouched
-            assert np.array_equal(hC.numpy().reshape(n, ldc)[:, m:], sentinel.numpy().reshape(n, ldc)[:, m:])
+        for native in (True, False):
+            hC.copy_(sentinel)
+            g8.gemm_host(opA, opB, m, n, k, 1.0, hA, lda, hB, ldb, beta, hC, ldc, num_moduli=N, fastmode=fast, chunk=256, native=native)
+            got = hC.numpy().reshape(n, ldc)[:, :m].T.copy()
+            assert H.bits_equal(got, want), H.first_diff(got, want, f"C {opA}{opB} native={native}")
+            if ldc > m:  # padding rows of the caller's buffer must be untouched
+                assert np.array_equal(hC.numpy().reshape(n, ldc)[:, m:], sentinel.numpy().reshape(n, ldc)[:, m:])
+
+
+@pytest.mark.parametrize("dtype,N,be", [(np.float64, 14, 0), (np.float32, 6, 0), (np.complex128, 11, 0), (np.complex64, 6, 0), (np.float64, 12, 1),
+                                         (np.complex128, 9, 1)])
+@pytest.mark.parametrize("fast", [False, True])
+def test_native_host_pipeline_all_types_bitwise(env, dtype, N, be, fast):
+    """g8_gemm_host (C ABI, csrc/g8_host.cu): every type, both backends, N/T/C operands, leading dimensions beyond the matrix, beta != 0,
+    a chunk size that leaves a ragged last chunk, pageable AND pinned host memory, and plan re-use -- all bit-identical to g8_gemm"""
+    torch, H = env.torch, env.H
+    import gemmul8_b200 as g8
+
+    rng = np.random.default_rng(23)
+    m, n, k = 150, 600, 1100   # k_pad / 128 = 9 tiles: the cluster-fused accurate stage (i) runs with a ragged split of the tiles
+    cplx = np.dtype(dtype).kind == "c"
+    for opA, opB, alpha, beta, pad, pinned in (("N", "N", 1.0, 0.0, 0, True), ("T", "C" if cplx else "T", 0.75, -0.5, 3, True), ("C" if cplx else "T", "N", 1.0, 1.0, 0, False)):
+        A = H.rand_matrix(rng, H.stored_shape(opA, m, k), dtype)
+        B = H.rand_matrix(rng, H.stored_shape(opB, k, n), dtype)
+        C0 = H.rand_matrix(rng, (m, n), dtype)
+        lda, ldb, ldc = A.shape[0] + pad, B.shape[0] + pad, m + pad
+        want = H.run_gemm(A, B, opA, opB, N, fast, alpha=alpha, beta=beta, C0=C0, lda=lda, ldb=ldb, ldc=ldc, backend=be)
+        dA, _ = H.to_dev_colmajor(A, lda)
+        dB, _ = H.to_dev_colmajor(B, ldb)
+        dC, _ = H.to_dev_colmajor(C0, ldc)
+        hA, hB, hC0 = dA.cpu(), dB.cpu(), dC.cpu()
+        if pinned:
+            hA, hB, hC0 = hA.pin_memory(), hB.pin_memory(), hC0.pin_memory()
+        plan = g8.NativeHostGemm(m, n, k, H.NP2T[np.dtype(dtype)], N, fast, opA, opB, chunk=256, backend=be)
+        for rep in range(2):   # the second call re-uses the plan's buffers, streams and events
+            hC = hC0.clone()
+            if pinned:
+                hC = hC.pin_memory()
+            plan.run(hA, hB, hC, alpha, beta, lda, ldb, ldc)
+            torch.cuda.synchronize()
+            got = hC.numpy().reshape(n, ldc)[:, :m].T.copy()
+            assert H.bits_equal(got, want), H.first_diff(got, want, f"C {opA}{opB} rep={rep}")
+            if pad:
+                assert np.array_equal(hC.numpy().reshape(n, ldc)[:, m:], hC0.numpy().reshape(n, ldc)[:, m:])
+        plan.close()
 
 
 @pytest.mark.parametrize("nparts", [2, 8])
