@@ -46,6 +46,7 @@ SYMBOLS = {
                                      c_size_t, c_void_p]),
     "g8_stage_maxabs_i32": (c_int, [c_void_p, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p]),
     "g8_stage_maxabs_i32_parts": (c_int, [c_void_p, c_int, c_size_t, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "g8_stage_gemm_bound_chain": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_size_t, c_int, c_void_p, c_void_p, c_void_p]),
     "g8_stage_gemm_scatter": (c_int, [c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_size_t, c_int, c_int,
                                       ctypes.POINTER(c_void_p), c_int, c_int, c_size_t, c_size_t, c_void_p]),
     "g8_peer_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p), c_void_p]),

@@ -653,6 +653,20 @@ __attribute__((visibility("default"))) int g8_stage_maxabs_i32_parts(const int32
     return (int)cudaGetLastError();
 }
 
+// bound GEMM of accurate mode over `chain` K-slabs: plane c of A_planes / B_planes (strideA / strideB bytes apart) holds K-slab c of the
+// int8 bound matrices; the accumulator sums all slabs, the epilogue reduces row / column maxima (never written).  INT8 backend, real.
+__attribute__((visibility("default"))) int g8_stage_gemm_bound_chain(const int8_t *A_planes, size_t strideA, const int8_t *B_planes, size_t strideB, size_t m, size_t n,
+                                                                      size_t k_pad, int chain, int32_t *rowmax, int32_t *colmax, void *stream) {
+    if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
+    if (!A_planes || !B_planes || !rowmax || !colmax || k_pad % 256 || chain < 1 || chain > 64) return G8_STATUS_INVALID_VALUE;
+    if ((size_t)chain * k_pad > (size_t(1) << 19)) return G8_STATUS_INVALID_VALUE; // bound entries <= 64: |sum| <= K * 2^12 < 2^31
+    GemmArgs g{};
+    g.A = A_planes, g.B = B_planes, g.strideA = strideA, g.strideB = strideB, g.m = m, g.n = n, g.m_pad = pad256(m), g.k_pad = k_pad;
+    g.num_units = 1, g.first_modulus = 0, g.epi = EPI_BOUND_MAX, g.kchain = chain;
+    g.ldc = pad256(m), g.rowmax = rowmax, g.colmax = colmax, g.k_true = (int)k_pad;
+    return launch_gemm_tc(g, static_cast<cudaStream_t>(stream));
+}
+
 // ---- fused GEMM -> scatter over peer memory (K-sharded multi-GPU) ----
 __attribute__((visibility("default"))) int g8_stage_gemm_scatter(int epilogue, const int8_t *A_lo, size_t strideA, const int8_t *B_lo, size_t strideB, size_t m, size_t n,
                                                                   size_t k_pad, int num_units, int first_modulus, void *const *peer_out, int world, int rank,

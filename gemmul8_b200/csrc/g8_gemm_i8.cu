@@ -270,6 +270,7 @@ struct KParams {
     void *peer_out[G8_MAX_PEERS];
     int owner_cols;
     int prods, set_stride; // EPI_F8_PROD
+    int kchain; // EPI_BOUND_MAX only: the accumulator sums `kchain` plane pairs (plane c of both operands = K-slab c of a K-sharded bound product)
     int group;  // lane tiles per rasterisation band (tile_coord)
     int tl_rot; // rotation of the lane-tile sweep so that the ranks do not all target the same owner at the same time
 };
@@ -347,8 +348,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
             uint32_t phase = 0;
             for (int t = cid; t < total_tiles; t += ncl) {
                 const TileCoord tc = tile_coord(t, P.tiles_l, P.tiles_c, P.tl_rot, P.group);
+                const int nchain = (EPI == EPI_BOUND_MAX) ? P.kchain : EC::NCHAIN;
                 for (int acc = 0; acc < EC::NACC; ++acc)
-                    for (int c = 0; c < EC::NCHAIN; ++c) {
+                    for (int c = 0; c < nchain; ++c) {
                         int planeA, planeB;
                         if constexpr (EPI == EPI_F8_PROD) {
                             // unit -> (modulus, product); product q = 3 * (plane set: Re, Im, Re+Im) + piece product
@@ -368,6 +370,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                             // Re / Im / Re+Im of BOTH operands selected by q
                             const int q = tc.unit % P.prods, mu = tc.unit / P.prods;
                             planeA = P.groupA[q] + mu, planeB = P.groupB[q] + mu;
+                        } else if constexpr (EPI == EPI_BOUND_MAX) {
+                            planeA = P.groupA[0] + tc.unit + c, planeB = P.groupB[0] + tc.unit + c; // chained K-slabs (c = 0 only in the single-GPU call)
                         } else {
                             int ga, gb;
                             chain_groups<EPI>(acc, c, ga, gb);
@@ -405,7 +409,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * TILE_COL;
                     uint32_t accumulate   = 0;
-                    for (int c = 0; c < EC::NCHAIN; ++c)
+                    const int nchain      = (EPI == EPI_BOUND_MAX) ? P.kchain : EC::NCHAIN;
+                    for (int c = 0; c < nchain; ++c)
                         for (int kb = 0; kb < P.kblocks; ++kb) {
                             mbar_wait(&full_bar[stage], phase);
                             tc_fence_after();
@@ -818,6 +823,7 @@ template <int EPI, int CG> static int launch_tc_cg(const GemmArgs &g, cudaStream
     int planes = g.num_units;
     const int mods = (EPI == EPI_MOD_I8 && g.prods > 1) ? (g.num_units + g.prods - 1) / g.prods : g.num_units;
     for (int i = 0; i < 3; ++i) planes = max(planes, max(g.groupA[i], g.groupB[i]) + mods);
+    if (EPI == EPI_BOUND_MAX) planes = max(planes, max(g.groupA[0], g.groupB[0]) + g.num_units - 1 + max(1, g.kchain));
     if (EPI == EPI_F8_MOD) planes = max(g.groupA[0], g.groupB[0]) + f8_plane_base(g.first_modulus + g.num_units);
     if (EPI == EPI_F8_PROD) planes = (g.prods / 3 - 1) * g.set_stride + f8_plane_base(g.first_modulus + (g.num_units + g.prods - 1) / g.prods);
     CUtensorMap mapL, mapC;
@@ -836,6 +842,7 @@ template <int EPI, int CG> static int launch_tc_cg(const GemmArgs &g, cudaStream
     P.rowmax = g.rowmax, P.colmax = g.colmax;
     P.inflate = (float)(g.k_true + 1) * 0x1p-24f;
     P.owner_cols = 0, P.tl_rot = 0;
+    P.kchain = g.kchain > 0 ? g.kchain : 1;
     static const int group_pref = [] { const char *e = getenv("G8_GEMM_GROUP"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 16; }();
     P.group = group_pref;
     P.prods = g.prods > 0 ? g.prods : (EPI == EPI_F8_PROD ? 3 : 1), P.set_stride = g.set_stride;

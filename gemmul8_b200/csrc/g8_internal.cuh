@@ -76,6 +76,8 @@ struct GemmArgs {
     // EPI_F8_PROD: products per modulus (3 real / 9 complex) and planes between the Re / Im / Re+Im plane sets;
     // EPI_MOD_I8: prods = 3 runs the three 3M products of a complex modulus as separate units (plane sets from groupA / groupB)
     int prods, set_stride;
+    // EPI_BOUND_MAX: number of plane pairs summed into the accumulator (K-sharded bound product over gathered K-slabs); 0 / 1 = one
+    int kchain;
 };
 // tcgen05 path (product).  Returns cudaError_t-compatible int.
 int launch_gemm_tc(const GemmArgs &g, cudaStream_t st);

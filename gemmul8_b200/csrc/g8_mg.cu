@@ -119,8 +119,9 @@ struct MgPlan {
     int16_t *sftA = nullptr, *sftB = nullptr;
     double *stat = nullptr;   // amax[m + n] | sumsq[m + n] | reduced copies
     int32_t *maxes = nullptr; // rowmax[m_pad] | colmax[n_pad] (input of the MAX all-reduce) | reduced copy
-    char *recv = nullptr;     // my receive area: [src rank][modulus][col in slab][row] int8, then (accurate) [src rank][col][row] int32
-    size_t recv_bytes = 0, cbar_off = 0;
+    char *recv = nullptr;     // my receive area: [src rank][modulus][col in slab][row] int8, then (accurate mode) the gathered bound
+                              // planes: A-bar [src rank][m_pad][k_pad] and the B-bar columns of MY slab [src rank][nc][k_pad]
+    size_t recv_bytes = 0, abar_off = 0, bbar_off = 0;
     char *peer_recv[G8_MAX_PEERS] = {};
 };
 
@@ -192,8 +193,9 @@ static int plan_create(MgPlan **out, MgComm *c, int dtype, int opA, int opB, siz
 #undef G8_ALLOC
     cudaMemset(p->sftA, 0, sizeof(int16_t) * p->m_pad), cudaMemset(p->sftB, 0, sizeof(int16_t) * p->n_pad);
     const size_t per = (size_t)N * n * p->m_pad; // W shards x N moduli x nc columns x m_pad rows (int8)
-    p->cbar_off   = per;
-    p->recv_bytes = per + (fast ? 0 : sizeof(int32_t) * W * p->nc * p->m_pad);
+    p->abar_off   = per;
+    p->bbar_off   = per + W * p->sizeA;
+    p->recv_bytes = per + (fast ? 0 : W * p->sizeA + W * p->nc * p->k_pad);
     unsigned char handle[64];
     if (int e = g8_peer_alloc(p->recv_bytes, reinterpret_cast<void **>(&p->recv), handle)) return fail(e);
     std::vector<unsigned char> all(64 * W);
@@ -228,20 +230,25 @@ static int run(MgPlan &p, const void *alpha, const void *A, size_t lda, const vo
         G8_TRY(g8_stage_shift_from_stats(amax_r, ss_r, m, N, 0, p.sftA, pst));
         G8_TRY(g8_stage_shift_from_stats(amax_r + m, ss_r + m, n, N, 0, p.sftB, pst));
     } else {
-        // accurate: s0 from the global max, bound planes (aliasing plane 0), INT32 bound partial scattered to the owners, slab maxima
-        // of the SUM over the shards, MAX all-reduce of [row maxima | column maxima], final shifts
+        // accurate: s0 from the global max, bound planes (aliasing plane 0).  The int8 bound planes are exchanged instead of INT32
+        // partial products (4x .. 16x fewer bytes): every rank receives all K-slabs of A-bar and the K-slabs of ITS column slab of B-bar
+        // (plain peer copies on the copy engines), multiplies them over the FULL K with the maxima fused into the GEMM epilogue, then
+        // one MAX all-reduce of [row maxima | column maxima] gives everybody the final shifts.
         G8_TRY(g8_stage_shift_from_stats(amax_r, nullptr, m, N, 1, p.sftA, pst));
         G8_TRY(g8_stage_shift_from_stats(amax_r + m, nullptr, n, N, 1, p.sftB, pst));
         G8_TRY(g8_stage_split(p.dtype, 1, p.opA, m, k, A, lda, N, 3, p.sftA, p.A_lo, p.sizeA, N, pst));
         G8_TRY(g8_stage_split(p.dtype, 0, p.opB, n, k, B, ldb, N, 3, p.sftB, p.B_lo, p.sizeB, N, pst));
-        const size_t slab = nc * mp;
-        void *tbl[G8_MAX_PEERS];
-        for (size_t o = 0; o < W; ++o) tbl[o] = p.peer_recv[o] + p.cbar_off + sizeof(int32_t) * (size_t)c.rank * slab;
-        G8_TRY(g8_stage_gemm_scatter(1 /*raw int32*/, p.A_lo, p.sizeA, p.B_lo, p.sizeB, m, n, p.k_pad, 1, 0, tbl, (int)W, c.rank, 0, mp, pst));
+        const size_t bslab = nc * p.k_pad;
+        for (size_t j = 0; j < W; ++j) {
+            const size_t o = ((size_t)c.rank + j) % W; // staggered targets
+            G8_TRY(cudaMemcpyAsync(p.peer_recv[o] + p.abar_off + (size_t)c.rank * p.sizeA, p.A_lo, p.sizeA, cudaMemcpyDefault, st));
+            G8_TRY(cudaMemcpyAsync(p.peer_recv[o] + p.bbar_off + (size_t)c.rank * bslab, p.B_lo + o * bslab, bslab, cudaMemcpyDefault, st));
+        }
         G8_TRY(comm_barrier(c, st));
         int32_t *mx = p.maxes, *mx_r = p.maxes + (p.m_pad + p.n_pad);
         G8_TRY(cudaMemsetAsync(mx, 0, sizeof(int32_t) * (p.m_pad + p.n_pad), st));
-        G8_TRY(g8_stage_maxabs_i32_parts(reinterpret_cast<const int32_t *>(p.recv + p.cbar_off), (int)W, slab, m, nc, mp, mx, mx + p.m_pad + (size_t)c.rank * nc, pst));
+        G8_TRY(g8_stage_gemm_bound_chain(reinterpret_cast<const int8_t *>(p.recv + p.abar_off), p.sizeA, reinterpret_cast<const int8_t *>(p.recv + p.bbar_off), bslab, m,
+                                         nc, p.k_pad, (int)W, mx, mx + p.m_pad + (size_t)c.rank * nc, pst));
         G8_TRY((comm_allreduce<int32_t, 0>(c, mx, mx_r, p.m_pad + p.n_pad, st)));
         G8_TRY(g8_stage_finalize_shift(p.sftA, mx_r, m, N, pst));
         G8_TRY(g8_stage_finalize_shift(p.sftB, mx_r + p.m_pad, n, N, pst));

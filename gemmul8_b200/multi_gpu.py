@@ -90,6 +90,11 @@ class CudaStages:
         api._check(self.lib.g8_stage_gemm_scatter(epi, A_lo.data_ptr(), strideA, B_lo.data_ptr(), strideB, m, n, k_pad, units, first, tbl, W,
                                                   peers.rank, out_stride, ldc, self._s()), "gemm_scatter")
 
+    def gemm_bound_chain(self, A_planes, strideA, B_planes, strideB, m, n, k_pad, chain, rowmax, colmax):
+        """bound GEMM over `chain` gathered K-slabs (plane c = slab c) with the row / column maxima fused into the epilogue"""
+        api._check(self.lib.g8_stage_gemm_bound_chain(A_planes.data_ptr(), strideA, B_planes.data_ptr(), strideB, m, n, k_pad, chain, rowmax.data_ptr(),
+                                                      colmax.data_ptr(), self._s()), "gemm_bound_chain")
+
     def gemm_bound(self, A_lo, strideA, B_lo, strideB, m, n, k_pad, rowmax, colmax):
         """bound GEMM of accurate mode with the row / column maxima fused into the epilogue (the bound product is never written)"""
         api._check(self.lib.g8_stage_gemm(2, 0, A_lo.data_ptr(), strideA, B_lo.data_ptr(), strideB, m, n, k_pad, 1, 0, None, None, None, 0,
@@ -247,16 +252,23 @@ class KShardGemm:
             # (accurate mode) by [src rank][col in slab][row] int32 for the bound partial
             self.recv_bytes = per
             self.cbar_off = per
-            total = per + (0 if self.fast else 4 * self.W * self.nc * self.m_pad)
+            total = per + (0 if (self.fast or os.environ.get("G8_MG_BOUND", "planes") == "planes") else 4 * self.W * self.nc * self.m_pad)
             self.peers = st.peer_buffer(total, group)
             self.recv = self.peers.local[:per].view(torch.int8)
-            if not self.fast:
+            if total > per:
                 self.cbar_parts = self.peers.local[per:].view(torch.int32)
             self.token = st.zeros(1, torch.int32)
         else:
             self.part = st.empty(per, torch.int32 if variant == "int32" else torch.int8)      # per batch: [col][modulus in batch][row]
             self.recv = st.empty(per // self.W if variant == "int32" else per, self.part.dtype)  # my column slab (x world for residue)
-        if not self.fast and variant != "fused":
+        # accurate mode, bound product over the full K: "planes" (default) exchanges the int8 bound PLANES (all-gather of A-bar, all-to-all
+        # of the B-bar column slabs; 4-16x fewer bytes than INT32 partial products) and multiplies them locally with the maxima fused into
+        # the GEMM epilogue; "int32" (G8_MG_BOUND=int32) is the round-1 exchange of INT32 partials.
+        self.bound = os.environ.get("G8_MG_BOUND", "planes")
+        if not self.fast and self.bound == "planes":
+            self.abar_all = st.empty(self.W * self.sizeA, torch.int8)
+            self.bbar_slabs = st.empty(self.W * self.nc * self.k_pad, torch.int8)
+        if not self.fast and variant != "fused" and self.bound != "planes":
             self.cbar = st.empty(n * self.m_pad, torch.int32)
             self.cbar_slab = st.empty(self.nc * self.m_pad, torch.int32)
         self.local_out_elems = m * self.nc
@@ -287,7 +299,15 @@ class KShardGemm:
         self._mark("bound planes")
         rowmax = st.zeros(self.m_pad, torch.int32)
         colmax_slab = st.zeros(self.nc, torch.int32)
-        if self.variant == "fused":
+        if self.bound == "planes":
+            if _is_gloo(self.group):
+                dist.all_gather(list(self.abar_all.view(self.W, self.sizeA).unbind(0)), self.A_lo[:self.sizeA].contiguous(), group=self.group)
+            else:
+                dist.all_gather_into_tensor(self.abar_all, self.A_lo[:self.sizeA], group=self.group)
+            all_to_all(self.bbar_slabs, self.B_lo[:self.sizeB], self.group)
+            self._mark("bound plane exchange")
+            st.gemm_bound_chain(self.abar_all, self.sizeA, self.bbar_slabs, self.nc * self.k_pad, m, self.nc, self.k_pad, self.W, rowmax, colmax_slab)
+        elif self.variant == "fused":
             # INT32 bound partial scattered by the GEMM epilogue into the owners' [src rank][col][row] areas, then summed + maxed there
             slab = self.nc * self.m_pad
             st.gemm_scatter(1, self.A_lo, self.sizeA, self.B_lo, self.sizeB, m, n, self.k_pad, 1, self.peers,

@@ -122,6 +122,12 @@ int g8_stage_maxabs_i32(const int32_t *C, size_t rows, size_t cols, size_t ld, i
 int g8_stage_maxabs_i32_parts(const int32_t *parts, int nparts, size_t part_stride, size_t rows, size_t cols, size_t ld, int32_t *rowmax,
                               int32_t *colmax, void *stream);
 
+/* Bound GEMM of accurate mode over `chain` GATHERED K-slabs (K-sharded multi-GPU): plane c of A_planes (k_pad x pad256(m), K-major,
+ * strideA bytes apart) and of B_planes (k_pad x n) is K-slab c of the int8 bound matrices; one accumulator sums all slabs and the
+ * epilogue reduces rowmax[r] / colmax[c] with atomicMax -- the bound product is never written and no INT32 partial is exchanged. */
+int g8_stage_gemm_bound_chain(const int8_t *A_planes, size_t strideA, const int8_t *B_planes, size_t strideB, size_t m, size_t n, size_t k_pad,
+                              int chain, int32_t *rowmax, int32_t *colmax, void *stream);
+
 /* Fused GEMM -> scatter over NVLink peer memory (no reference counterpart; replaces "GEMM, then NCCL all-to-all / reduce-scatter"):
  * the tcgen05 epilogue stores columns [o*n/world, (o+1)*n/world) of every unit's product directly into peer_out[o], a buffer of
  * rank o mapped with g8_peer_open (peer_out[rank] is this rank's own buffer), at column (c - o*n/world), leading dimension ldc,

@@ -81,6 +81,13 @@ class OracleStages:
         rowmax[:m] = torch.from_numpy(np.maximum(rowmax.numpy()[:m], H.max(axis=1, initial=0)).astype(np.int32))
         colmax[:n] = torch.from_numpy(np.maximum(colmax.numpy()[:n], H.max(axis=0, initial=0)).astype(np.int32))
 
+    def gemm_bound_chain(self, A_planes, strideA, B_planes, strideB, m, n, k_pad, chain, rowmax, colmax):
+        a, b = A_planes.numpy(), B_planes.numpy()
+        H = sum(a[c * strideA:c * strideA + m * k_pad].reshape(m, k_pad).astype(np.int64) @ b[c * strideB:c * strideB + n * k_pad].reshape(n, k_pad).astype(np.int64).T
+                for c in range(chain))
+        rowmax[:m] = torch.from_numpy(np.maximum(rowmax.numpy()[:m], H.max(axis=1, initial=0)).astype(np.int32))
+        colmax[:n] = torch.from_numpy(np.maximum(colmax.numpy()[:n], H.max(axis=0, initial=0)).astype(np.int32))
+
     def maxabs_parts(self, parts, nparts, part_stride, rows, cols, ld, rowmax, colmax):
         p = parts.numpy().astype(np.int64)
         tot = sum(p[q * part_stride:q * part_stride + cols * ld] for q in range(nparts)).astype(np.int32)
@@ -198,8 +205,8 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, variant, fast, dtype_name, q, sum_in_crt="1"):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), G8_MG_SUM_IN_CRT=sum_in_crt)
+def _worker(rank, world, port, variant, fast, dtype_name, q, sum_in_crt="1", bound="planes"):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), G8_MG_SUM_IN_CRT=sum_in_crt, G8_MG_BOUND=bound)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from gemmul8_b200 import multi_gpu
@@ -237,14 +244,16 @@ def _worker(rank, world, port, variant, fast, dtype_name, q, sum_in_crt="1"):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("variant", ["int32", "residue", "fused"])
+@pytest.mark.parametrize("variant,bound", [("int32", "planes"), ("residue", "planes"), ("fused", "planes"), ("fused", "int32"), ("residue", "int32")])
 @pytest.mark.parametrize("fast", [False, True])
 @pytest.mark.parametrize("dtype_name", ["float64", "float32"])
-def test_kshard_two_ranks_matches_single_process(variant, fast, dtype_name):
+def test_kshard_two_ranks_matches_single_process(variant, bound, fast, dtype_name):
+    if fast and bound == "int32":
+        pytest.skip("the bound exchange only exists in accurate mode")
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, variant, fast, dtype_name, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, variant, fast, dtype_name, q, "1", bound)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in range(world)]
