@@ -586,6 +586,8 @@ def main():
             del Cn
     elif shard == "k" and not args.no_extras and (args.k_local == 0 and args.size == 0):
         # the round-1 weak-K workload (8192 x 8192 x 8192 N) for continuity
+        if hasattr(mg, "close"):
+            mg.close()
         del mg, A, B, C, hA, hB, hC
         torch.cuda.empty_cache()
         m = n = S2 = 8192

@@ -75,7 +75,9 @@ __global__ void __launch_bounds__(256) crt_kernel(CrtArgs c, Scalars hs, size_t 
     const int hi52 = 0x43300000 | (int)(total >> 63);
     double tmplA = __hiloint2double(hi52, 0), tmplB = __hiloint2double(hi52, 1); // see splice_low
     const int8_t *sp = src; // plane i: sp = src + i * pstride, advanced by addition (no 64-bit multiply per plane)
-#pragma unroll 4
+    // planes in flight per thread: 4 for the plain C_mid; K-sharded: PARTS loads per plane, so fewer planes (>= 8 loads in flight)
+    constexpr int UNR = PARTS >= 8 ? 1 : PARTS >= 4 ? 2 : 4;
+#pragma unroll UNR
     for (int i = 0; i < N; ++i, sp += pstride) {
         double cd[NV];
         if constexpr (BE == INT8) {

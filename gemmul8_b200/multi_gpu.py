@@ -56,6 +56,18 @@ class CudaStages:
     def _s(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
 
+    # The A side and the B side of the preprocessing are independent: `with st.side():` runs the enclosed launches on a helper stream
+    # forked from the current one; st.join() makes the current stream wait for it.  (CPU test stages implement both as no-ops.)
+    def side(self):
+        if not hasattr(self, "_side"):
+            self._side = torch.cuda.Stream(self.dev)
+        self._side.wait_stream(torch.cuda.current_stream(self.dev))
+        return torch.cuda.stream(self._side)
+
+    def join(self):
+        if hasattr(self, "_side"):
+            torch.cuda.current_stream(self.dev).wait_stream(self._side)
+
     def empty(self, n, dtype):
         return torch.empty(n, dtype=dtype, device=self.dev)
 
@@ -280,7 +292,9 @@ class KShardGemm:
     def _shifts(self, A, B):
         st, m, n, k, N = self.st, self.m, self.n, self.k, self.N
         amaxA, ssA = st.stats(True, 0, m, k, A, m)
-        amaxB, ssB = st.stats(False, 0, n, k, B, k)
+        with st.side():
+            amaxB, ssB = st.stats(False, 0, n, k, B, k)
+        st.join()
         self._mark("stats")
         both_max = torch.cat([amaxA, amaxB])
         dist.all_reduce(both_max, op=dist.ReduceOp.MAX, group=self.group)
@@ -295,7 +309,9 @@ class KShardGemm:
         st.shift_from_stats(amaxA.contiguous(), None, 1, self.sftA)
         st.shift_from_stats(amaxB.contiguous(), None, 1, self.sftB)
         st.split(True, 0, m, k, A, m, 3, self.sftA, self.A_lo, self.sizeA)
-        st.split(False, 0, n, k, B, k, 3, self.sftB, self.B_lo, self.sizeB)
+        with st.side():
+            st.split(False, 0, n, k, B, k, 3, self.sftB, self.B_lo, self.sizeB)
+        st.join()
         self._mark("bound planes")
         rowmax = st.zeros(self.m_pad, torch.int32)
         colmax_slab = st.zeros(self.nc, torch.int32)
@@ -360,7 +376,9 @@ class KShardGemm:
         self._shifts(A, B)
         self._mark("shifts")
         st.split(True, 0, m, k, A, m, 0, self.sftA, self.A_lo, self.sizeA)
-        st.split(False, 0, n, k, B, k, 0, self.sftB, self.B_lo, self.sizeB)
+        with st.side():
+            st.split(False, 0, n, k, B, k, 0, self.sftB, self.B_lo, self.sizeB)
+        st.join()
         self._mark("split")
         mp, nc, W = self.m_pad, self.nc, self.W
         if self.variant == "fused":

@@ -54,6 +54,13 @@ class OracleStages:
 
     scatter_granularity = 1
 
+    def side(self):      # the CUDA stages fork a helper stream here; on the CPU everything is sequential
+        import contextlib
+        return contextlib.nullcontext()
+
+    def join(self):
+        pass
+
     def peer_buffer(self, nbytes, group=None):
         return ShmPeerBuffer(nbytes, group)
 
