@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--backend", default="int8", choices=["int8", "fp8"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the power / native-DGEMM / tensor-ceiling / weak-K legs")
-    ap.add_argument("--mg-variant", default="fused", choices=["int32", "residue", "fused", "native"],
+    ap.add_argument("--mg-variant", default="native", choices=["int32", "residue", "fused", "native"],
                     help="K-shard exchange: int32 / residue = NCCL collectives after the GEMM; fused = GEMM -> NVLink scatter kernel, orchestrated "
                          "from Python with NCCL for the small vectors; native = the same kernels driven by the C ABI g8_gemm_mg (no NCCL, no Python)")
     ap.add_argument("--mg-shard", default="k", choices=["k", "n", "mod"],

@@ -123,6 +123,9 @@ struct MgPlan {
                               // planes: A-bar [src rank][m_pad][k_pad] and the B-bar columns of MY slab [src rank][nc][k_pad]
     size_t recv_bytes = 0, abar_off = 0, bbar_off = 0;
     char *peer_recv[G8_MAX_PEERS] = {};
+    // helper stream for the B side of the preprocessing (forked from / joined into the caller's stream inside every call)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 #define G8_TRY(x)                              \
@@ -139,6 +142,9 @@ static void plan_free(MgPlan *p) {
         for (int o = 0; o < p->comm->world; ++o)
             if (o != p->comm->rank && p->peer_recv[o]) cudaIpcCloseMemHandle(p->peer_recv[o]);
     if (p->recv) cudaFree(p->recv);
+    if (p->side) cudaStreamDestroy(p->side);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
     delete p;
 }
 
@@ -192,6 +198,9 @@ static int plan_create(MgPlan **out, MgComm *c, int dtype, int opA, int opB, siz
     G8_ALLOC(p->maxes, sizeof(int32_t) * 2 * (p->m_pad + p->n_pad));
 #undef G8_ALLOC
     cudaMemset(p->sftA, 0, sizeof(int16_t) * p->m_pad), cudaMemset(p->sftB, 0, sizeof(int16_t) * p->n_pad);
+    if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess)
+        return fail((int)cudaErrorUnknown);
     const size_t per = (size_t)N * n * p->m_pad; // W shards x N moduli x nc columns x m_pad rows (int8)
     p->abar_off   = per;
     p->bbar_off   = per + W * p->sizeA;
@@ -221,27 +230,47 @@ static int run(MgPlan &p, const void *alpha, const void *A, size_t lda, const vo
     double *amax = p.stat, *ss = p.stat + (m + n), *amax_r = p.stat + 2 * (m + n), *ss_r = p.stat + 3 * (m + n);
     void *pst = st;
 
+    // The A side and the B side are independent until they meet in a GEMM: B-side kernels run on the plan's helper stream
+    // (fork: it waits for `st`; join: `st` waits for it), which also lets the A-bar peer copies overlap the B-bar kernel.
+    void *psd = p.side;
+    auto fork = [&]() -> int {
+        G8_TRY(cudaEventRecord(p.ev_fork, st));
+        return (int)cudaStreamWaitEvent(p.side, p.ev_fork, 0);
+    };
+    auto join = [&]() -> int {
+        G8_TRY(cudaEventRecord(p.ev_join, p.side));
+        return (int)cudaStreamWaitEvent(st, p.ev_join, 0);
+    };
+
     // ---- shifts from GLOBAL row statistics ----
+    G8_TRY(fork());
     G8_TRY(g8_stage_stats(p.dtype, 1, p.opA, m, k, A, lda, amax, ss, pst));
-    G8_TRY(g8_stage_stats(p.dtype, 0, p.opB, n, k, B, ldb, amax + m, ss + m, pst));
+    G8_TRY(g8_stage_stats(p.dtype, 0, p.opB, n, k, B, ldb, amax + m, ss + m, psd));
+    G8_TRY(join());
     G8_TRY((comm_allreduce<double, 0>(c, amax, amax_r, m + n, st)));
     if (p.fast) {
         G8_TRY((comm_allreduce<double, 1>(c, ss, ss_r, m + n, st)));
+        G8_TRY(fork());
         G8_TRY(g8_stage_shift_from_stats(amax_r, ss_r, m, N, 0, p.sftA, pst));
-        G8_TRY(g8_stage_shift_from_stats(amax_r + m, ss_r + m, n, N, 0, p.sftB, pst));
+        G8_TRY(g8_stage_shift_from_stats(amax_r + m, ss_r + m, n, N, 0, p.sftB, psd));
     } else {
         // accurate: s0 from the global max, bound planes (aliasing plane 0).  The int8 bound planes are exchanged instead of INT32
         // partial products (4x .. 16x fewer bytes): every rank receives all K-slabs of A-bar and the K-slabs of ITS column slab of B-bar
         // (plain peer copies on the copy engines), multiplies them over the FULL K with the maxima fused into the GEMM epilogue, then
         // one MAX all-reduce of [row maxima | column maxima] gives everybody the final shifts.
+        G8_TRY(fork());
         G8_TRY(g8_stage_shift_from_stats(amax_r, nullptr, m, N, 1, p.sftA, pst));
-        G8_TRY(g8_stage_shift_from_stats(amax_r + m, nullptr, n, N, 1, p.sftB, pst));
         G8_TRY(g8_stage_split(p.dtype, 1, p.opA, m, k, A, lda, N, 3, p.sftA, p.A_lo, p.sizeA, N, pst));
-        G8_TRY(g8_stage_split(p.dtype, 0, p.opB, n, k, B, ldb, N, 3, p.sftB, p.B_lo, p.sizeB, N, pst));
+        G8_TRY(g8_stage_shift_from_stats(amax_r + m, nullptr, n, N, 1, p.sftB, psd));
+        G8_TRY(g8_stage_split(p.dtype, 0, p.opB, n, k, B, ldb, N, 3, p.sftB, p.B_lo, p.sizeB, N, psd));
         const size_t bslab = nc * p.k_pad;
-        for (size_t j = 0; j < W; ++j) {
+        for (size_t j = 0; j < W; ++j) { // A-bar travels while the B-bar kernel still runs on the helper stream
             const size_t o = ((size_t)c.rank + j) % W; // staggered targets
             G8_TRY(cudaMemcpyAsync(p.peer_recv[o] + p.abar_off + (size_t)c.rank * p.sizeA, p.A_lo, p.sizeA, cudaMemcpyDefault, st));
+        }
+        G8_TRY(join());
+        for (size_t j = 0; j < W; ++j) {
+            const size_t o = ((size_t)c.rank + j) % W;
             G8_TRY(cudaMemcpyAsync(p.peer_recv[o] + p.bbar_off + (size_t)c.rank * bslab, p.B_lo + o * bslab, bslab, cudaMemcpyDefault, st));
         }
         G8_TRY(comm_barrier(c, st));
@@ -250,13 +279,15 @@ static int run(MgPlan &p, const void *alpha, const void *A, size_t lda, const vo
         G8_TRY(g8_stage_gemm_bound_chain(reinterpret_cast<const int8_t *>(p.recv + p.abar_off), p.sizeA, reinterpret_cast<const int8_t *>(p.recv + p.bbar_off), bslab, m,
                                          nc, p.k_pad, (int)W, mx, mx + p.m_pad + (size_t)c.rank * nc, pst));
         G8_TRY((comm_allreduce<int32_t, 0>(c, mx, mx_r, p.m_pad + p.n_pad, st)));
+        G8_TRY(fork());
         G8_TRY(g8_stage_finalize_shift(p.sftA, mx_r, m, N, pst));
-        G8_TRY(g8_stage_finalize_shift(p.sftB, mx_r + p.m_pad, n, N, pst));
+        G8_TRY(g8_stage_finalize_shift(p.sftB, mx_r + p.m_pad, n, N, psd));
     }
 
-    // ---- local split with the global shifts, contraction fused with the exchange, owner-side sum + CRT ----
+    // ---- local split with the global shifts (A on `st`, B on the helper stream), contraction fused with the exchange, owner-side sum + CRT ----
     G8_TRY(g8_stage_split(p.dtype, 1, p.opA, m, k, A, lda, N, 0, p.sftA, p.A_lo, p.sizeA, N, pst));
-    G8_TRY(g8_stage_split(p.dtype, 0, p.opB, n, k, B, ldb, N, 0, p.sftB, p.B_lo, p.sizeB, N, pst));
+    G8_TRY(g8_stage_split(p.dtype, 0, p.opB, n, k, B, ldb, N, 0, p.sftB, p.B_lo, p.sizeB, N, psd));
+    G8_TRY(join());
     {
         void *tbl[G8_MAX_PEERS];
         for (size_t o = 0; o < W; ++o) tbl[o] = p.peer_recv[o] + (size_t)c.rank * N * nc * mp;

@@ -311,20 +311,22 @@ class KShardGemm:
         st.split(True, 0, m, k, A, m, 3, self.sftA, self.A_lo, self.sizeA)
         with st.side():
             st.split(False, 0, n, k, B, k, 3, self.sftB, self.B_lo, self.sizeB)
-        st.join()
-        self._mark("bound planes")
         rowmax = st.zeros(self.m_pad, torch.int32)
         colmax_slab = st.zeros(self.nc, torch.int32)
         if self.bound == "planes":
+            # A-bar travels (all-gather, the bulk of the exchange) while the B-bar kernel still runs on the helper stream
             if _is_gloo(self.group):
                 dist.all_gather(list(self.abar_all.view(self.W, self.sizeA).unbind(0)), self.A_lo[:self.sizeA].contiguous(), group=self.group)
             else:
                 dist.all_gather_into_tensor(self.abar_all, self.A_lo[:self.sizeA], group=self.group)
+            st.join()
+            self._mark("bound planes + A-bar gather")
             all_to_all(self.bbar_slabs, self.B_lo[:self.sizeB], self.group)
-            self._mark("bound plane exchange")
+            self._mark("B-bar slab exchange")
             st.gemm_bound_chain(self.abar_all, self.sizeA, self.bbar_slabs, self.nc * self.k_pad, m, self.nc, self.k_pad, self.W, rowmax, colmax_slab)
         elif self.variant == "fused":
             # INT32 bound partial scattered by the GEMM epilogue into the owners' [src rank][col][row] areas, then summed + maxed there
+            st.join()
             slab = self.nc * self.m_pad
             st.gemm_scatter(1, self.A_lo, self.sizeA, self.B_lo, self.sizeB, m, n, self.k_pad, 1, self.peers,
                             self.cbar_off + 4 * self.rank * slab, 0, self.m_pad)
@@ -332,6 +334,7 @@ class KShardGemm:
             self._rank_barrier()
             st.maxabs_parts(self.cbar_parts, self.W, slab, m, self.nc, self.m_pad, rowmax, colmax_slab)
         else:
+            st.join()
             st.gemm(1, self.A_lo, self.sizeA, self.B_lo, self.sizeB, m, n, self.k_pad, 1, self.cbar, 0, self.m_pad)
             reduce_scatter_sum(self.cbar_slab, self.cbar, self.group)
             st.maxabs(self.cbar_slab, m, self.nc, self.m_pad, rowmax, colmax_slab)

@@ -27,6 +27,11 @@ if has bench; then
   run accu_native --mode accu --mg-variant native --no-extras
   run fast_native --mode fast --mg-variant native --no-extras
 fi
+if has confirm; then
+  run default
+  TRACE=1 run accu_fused --mode accu --mg-variant fused --no-extras
+  run fast_native --mode fast --no-extras
+fi
 if has alt; then
   G8_MG_BOUND=int32 run accu_fused_boundint32 --mode accu --mg-variant fused --no-extras
   G8_MG_SUM_IN_CRT=0 run accu_fused_sumpass --mode accu --mg-variant fused --no-extras
