@@ -536,6 +536,20 @@ def main():
                 for key in ("gemm+scatter", "barrier", "sum+crt", "split"):
                     print(f"[mg trace all ranks] {key}:", [dict(t).get(key) for t in allr], file=sys.stderr)
     ms_e2e, _ = timed(step_e2e, max(2, min(args.steps, 5)), 1)
+    h2d_rank_gbps = None
+    if distributed:
+        # what bounds the multi-GPU e2e leg: all ranks pull their slabs from host memory at the same time (per-rank H2D rate, concurrent)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(3):
+            A.copy_(hA, non_blocking=True)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        mine = 3 * hA.numel() * 8 / (e0.elapsed_time(e1) * 1e-3) * 1e-9
+        allg = [None] * world
+        dist.all_gather_object(allg, round(mine, 1))
+        h2d_rank_gbps = allg
 
     flops = 2.0 * m * n_total * k_total
     value = flops / (ms_dev * 1e-3) * 1e-12
@@ -626,7 +640,9 @@ def main():
                    "l2": "inputs and residue planes are larger than the 126 MB L2; no explicit flush",
                    "timing": "CUDA events on the launch stream, max over ranks" + ("; median of 3 timed regions" if distributed else "")},
         "e2e": {"value": round(e2e_val, 2), "unit": "TFLOPS", "ms_per_step": round(ms_e2e, 3),
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                **({"h2d_gbps_per_rank_concurrent": h2d_rank_gbps, "note": "per-rank bytes; every rank copies its K-slabs from NUMA-local pinned memory at "
+                    "the same time: the host side (PCIe root complexes / memory) bounds the aggregate"} if h2d_rank_gbps else {})},
         "gpu_launches": launches_per_call * args.steps * (3 if distributed else 1),
         "clocks": clocks,
         "impl": args.impl,

@@ -45,8 +45,14 @@ fi
 if has harness; then
   # the reference's own benchmark harness (testing/test.cu, unmodified), linked against the reference library and against this repo's libgemmul8.a
   ( cd gpurun_out && mkdir -p harness_ref harness_ours
-    ( cd harness_ref && timeout 900 ../../oracle/_ref/harness_ref flops DGEMM INT8 > run.log 2>&1 )
-    ( cd harness_ours && GEMMUL8_PHASE_TIMING=1 timeout 900 ../../oracle/_ref/harness_ours flops DGEMM INT8 > run.log 2>&1 )
+    ( cd harness_ref && timeout 480 ../../oracle/_ref/harness_ref flops DGEMM INT8 > run.log 2>&1 )
+    ( cd harness_ours && GEMMUL8_PHASE_TIMING=1 timeout 480 ../../oracle/_ref/harness_ours flops DGEMM INT8 > run.log 2>&1 )
     tail -3 harness_ref/run.log harness_ours/run.log )
+fi
+if has fp8stats; then
+  timeout 600 python tools/fp8_shift_stats.py 8192 -1 1 2>&1 | tail -16
+fi
+if has sanitize; then
+  timeout 900 python tools/sanitizer_run.py 2>&1 | tail -12
 fi
 ls -la gpurun_out | tail -15
