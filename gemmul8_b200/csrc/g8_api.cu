@@ -435,6 +435,52 @@ __global__ void __launch_bounds__(256) i8_cplx_combine_kernel(const int8_t *__re
     dst[1]     = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
+// K-sharded complex INT8: the three 3M products of every modulus arrive as `nparts` per-shard residue arrays
+// [shard][modulus][rr, ii, ss][elems]; sum over the shards (dp4a against one-hot selectors), reduce mod p, then the 3M recombination
+__global__ void __launch_bounds__(256) i8_cplx_combine_parts_kernel(const int8_t *__restrict__ parts, int nparts, size_t part_stride, size_t elems_per_unit,
+                                                                    int first_modulus, int8_t *__restrict__ C_mid, size_t out_stride) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i * 16 >= elems_per_unit) return;
+    const int u = blockIdx.y, midx = first_modulus + u;
+    const int32_t p = g8d_moduli[INT8][midx], pinv = g8d_pinv32[INT8][midx];
+    const int8_t *src = parts + (size_t)u * 3 * elems_per_unit + i * 16;
+    int32_t acc[3][16];
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[q][j] = 0;
+    for (int s = 0; s < nparts; ++s) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int4 v   = __ldcs(reinterpret_cast<const int4 *>(src + (size_t)s * part_stride + (size_t)q * elems_per_unit));
+            const int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[q][j] = __dp4a(w[j >> 2], 1 << (8 * (j & 3)), acc[q][j]);
+        }
+    }
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int32_t rr = mod_i32(acc[0][j + e], p, pinv), ii = mod_i32(acc[1][j + e], p, pinv), ss = mod_i32(acc[2][j + e], p, pinv);
+            const int32_t re = mod_i32(rr - ii, p, pinv), im = mod_i32(ss - rr - ii, p, pinv);
+            word |= ((uint32_t)(re & 0xFF) | ((uint32_t)(im & 0xFF) << 8)) << (16 * e);
+        }
+        o[j >> 1] = word;
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(C_mid + ((size_t)u * out_stride + i * 16) * 2);
+    dst[0]     = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1]     = make_uint4(o[4], o[5], o[6], o[7]);
+}
+void launch_i8_cplx_combine_parts(const int8_t *parts, int nparts, size_t part_stride, size_t elems_per_unit, int num_units, int first_modulus, int8_t *C_mid,
+                                  size_t out_stride, cudaStream_t st) {
+    const size_t groups = elems_per_unit / 16;
+    const dim3 grid((unsigned)((groups + 255) / 256), (unsigned)num_units);
+    i8_cplx_combine_parts_kernel<<<grid, 256, 0, st>>>(parts, nparts, part_stride, elems_per_unit, first_modulus, C_mid, out_stride);
+}
+
 void launch_i8_cplx_combine(const int8_t *prod, size_t elems_per_unit, int num_units, int first_modulus, int8_t *C_mid, size_t out_stride,
                             cudaStream_t st) {
     const size_t groups = elems_per_unit / 16;

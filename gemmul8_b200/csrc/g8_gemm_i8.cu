@@ -22,6 +22,7 @@
 #include "g8_internal.cuh"
 
 #include <cuda.h> // CUtensorMap (types only; the encoder is fetched through the runtime, no -lcuda)
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
 
@@ -348,7 +349,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
             uint32_t phase = 0;
             for (int t = cid; t < total_tiles; t += ncl) {
                 const TileCoord tc = tile_coord(t, P.tiles_l, P.tiles_c, P.tl_rot, P.group);
-                const int nchain = (EPI == EPI_BOUND_MAX) ? P.kchain : EC::NCHAIN;
+                const int nchain = (EPI == EPI_BOUND_MAX) ? P.kchain : (EPI == EPI_BOUND_MAX_CPLX) ? 2 * P.kchain : EC::NCHAIN;
                 for (int acc = 0; acc < EC::NACC; ++acc)
                     for (int c = 0; c < nchain; ++c) {
                         int planeA, planeB;
@@ -365,13 +366,18 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                             const bool sq = idx < 6;
                             planeA = P.groupA[0] + base + (sq ? (acc == 0 ? 0 : 1) : acc); // group offset: 0 (real) or the Re / Im / Re+Im set
                             planeB = P.groupB[0] + base + (sq ? (acc == 1 ? 0 : 1) : acc);
-                        } else if constexpr (EPI == EPI_MOD_I8) {
+                        } else if constexpr (EPI == EPI_MOD_I8 || EPI == EPI_MOD_I8_SCATTER) {
                             // real: one product per modulus.  complex (prods = 3): unit -> (modulus, 3M product q) with the plane sets
                             // Re / Im / Re+Im of BOTH operands selected by q
                             const int q = tc.unit % P.prods, mu = tc.unit / P.prods;
                             planeA = P.groupA[q] + mu, planeB = P.groupB[q] + mu;
                         } else if constexpr (EPI == EPI_BOUND_MAX) {
                             planeA = P.groupA[0] + tc.unit + c, planeB = P.groupB[0] + tc.unit + c; // chained K-slabs (c = 0 only in the single-GPU call)
+                        } else if constexpr (EPI == EPI_BOUND_MAX_CPLX) {
+                            // K-slab c / 2 of the gathered planes [slab][|Re|, |Im|]; inside a slab the two products of chain_groups
+                            int ga, gb;
+                            chain_groups<EPI>(acc, c & 1, ga, gb);
+                            planeA = P.groupA[ga] + tc.unit + 2 * (c >> 1), planeB = P.groupB[gb] + tc.unit + 2 * (c >> 1);
                         } else {
                             int ga, gb;
                             chain_groups<EPI>(acc, c, ga, gb);
@@ -409,7 +415,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * TILE_COL;
                     uint32_t accumulate   = 0;
-                    const int nchain      = (EPI == EPI_BOUND_MAX) ? P.kchain : EC::NCHAIN;
+                    const int nchain      = (EPI == EPI_BOUND_MAX) ? P.kchain : (EPI == EPI_BOUND_MAX_CPLX) ? 2 * P.kchain : EC::NCHAIN;
                     for (int c = 0; c < nchain; ++c)
                         for (int kb = 0; kb < P.kblocks; ++kb) {
                             mbar_wait(&full_bar[stage], phase);
@@ -463,7 +469,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
             const int col_c   = tc.tl * (TILE_LANE * CG) + (int)rank * TILE_LANE + q * 32 + lane; // column of C owned by this thread
             const int row0    = tc.tc * TILE_COL;                  // first row of C of this tile
             const bool col_ok = col_c < P.n;
-            const int midx    = P.first_modulus + ((EPI == EPI_MOD_I8) ? tc.unit / P.prods : tc.unit);
+            const int midx    = P.first_modulus + ((EPI == EPI_MOD_I8 || EPI == EPI_MOD_I8_SCATTER) ? tc.unit / P.prods : tc.unit);
             // output base and column index inside it (peer scatter: the whole 256-column tile belongs to one owner)
             char *out_base = static_cast<char *>(P.out);
             int col_o      = col_c;
@@ -801,11 +807,14 @@ static bool make_plane_map(CUtensorMap *map, const void *base, size_t k_pad, siz
 }
 
 static int num_sms() {
-    static int n[64] = {};
+    static std::atomic<int> n[64]; // racing first calls store the same value
     int dev = 0;
     cudaGetDevice(&dev);
-    int &v = n[dev & 63];
-    if (!v) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    int v = n[dev & 63].load(std::memory_order_relaxed);
+    if (!v) {
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        n[dev & 63].store(v, std::memory_order_relaxed);
+    }
     return v;
 }
 
@@ -821,9 +830,10 @@ static int cta_group_pref() {
 template <int EPI, int CG> static int launch_tc_cg(const GemmArgs &g, cudaStream_t st) {
     using KS = KernelShape<EPI, CG>;
     int planes = g.num_units;
-    const int mods = (EPI == EPI_MOD_I8 && g.prods > 1) ? (g.num_units + g.prods - 1) / g.prods : g.num_units;
+    const int mods = ((EPI == EPI_MOD_I8 || EPI == EPI_MOD_I8_SCATTER) && g.prods > 1) ? (g.num_units + g.prods - 1) / g.prods : g.num_units;
     for (int i = 0; i < 3; ++i) planes = max(planes, max(g.groupA[i], g.groupB[i]) + mods);
     if (EPI == EPI_BOUND_MAX) planes = max(planes, max(g.groupA[0], g.groupB[0]) + g.num_units - 1 + max(1, g.kchain));
+    if (EPI == EPI_BOUND_MAX_CPLX) planes = max(planes, 2 * max(1, g.kchain));
     if (EPI == EPI_F8_MOD) planes = max(g.groupA[0], g.groupB[0]) + f8_plane_base(g.first_modulus + g.num_units);
     if (EPI == EPI_F8_PROD) planes = (g.prods / 3 - 1) * g.set_stride + f8_plane_base(g.first_modulus + (g.num_units + g.prods - 1) / g.prods);
     CUtensorMap mapL, mapC;
@@ -855,14 +865,13 @@ template <int EPI, int CG> static int launch_tc_cg(const GemmArgs &g, cudaStream
     }
 
     // per kernel instantiation AND per device (function attributes are per-device state; one process may drive several GPUs)
-    static bool attr_set_dev[64] = {};
+    static std::atomic<bool> attr_set_dev[64];
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
-    bool &attr_set = attr_set_dev[cur_dev & 63];
-    if (!attr_set) {
+    if (!attr_set_dev[cur_dev & 63].load(std::memory_order_acquire)) { // setting it twice (two racing first calls) is harmless
         cudaError_t e = cudaFuncSetAttribute(gemm_i8_tc_kernel<EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, KS::SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        attr_set_dev[cur_dev & 63].store(true, std::memory_order_release);
     }
     const int total = P.num_units * P.tiles_l * P.tiles_c;
     const int grid  = CG * min(total, num_sms() / CG);

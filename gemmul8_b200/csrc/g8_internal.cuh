@@ -114,6 +114,9 @@ void launch_i8_cplx_combine(const int8_t *prod, size_t elems_per_unit, int num_u
                             cudaStream_t st);
 void launch_f8_combine(const int16_t *prod, bool cplx, size_t elems_per_unit, int num_units, int first_modulus, int16_t *C_mid, size_t out_stride,
                        cudaStream_t st);
+// K-sharded complex INT8: `nparts` per-shard arrays [modulus][rr, ii, ss][elems] (part_stride BYTES apart) -> summed, reduced, recombined
+void launch_i8_cplx_combine_parts(const int8_t *parts, int nparts, size_t part_stride, size_t elems_per_unit, int num_units, int first_modulus, int8_t *C_mid,
+                                  size_t out_stride, cudaStream_t st);
 
 // ---- orchestration pieces shared by g8_gemm (g8_api.cu), the host-buffer pipeline (g8_host.cu) and the multi-GPU driver (g8_mg.cu) ----
 struct ContractArgs {

@@ -115,7 +115,9 @@ struct MgPlan {
     int dtype = F64, opA = OP_N, opB = OP_N, fast = 0;
     size_t m = 0, n = 0, k = 0, m_pad = 0, k_pad = 0, n_pad = 0, nc = 0, sizeA = 0, sizeB = 0;
     unsigned N = 0;
-    int8_t *A_lo = nullptr, *B_lo = nullptr;
+    bool cplx = false;
+    size_t sets = 1, bsets = 1; // plane sets of the residues (Re, Im, Re+Im: 3 for complex) / of the bound planes (|Re|, |Im|: 2)
+    int8_t *A_lo = nullptr, *B_lo = nullptr, *C_mid = nullptr; // C_mid: complex only (owner-side 3M recombination before the CRT)
     int16_t *sftA = nullptr, *sftB = nullptr;
     double *stat = nullptr;   // amax[m + n] | sumsq[m + n] | reduced copies
     int32_t *maxes = nullptr; // rowmax[m_pad] | colmax[n_pad] (input of the MAX all-reduce) | reduced copy
@@ -136,7 +138,7 @@ struct MgPlan {
 
 static void plan_free(MgPlan *p) {
     if (!p) return;
-    for (void *q : {(void *)p->A_lo, (void *)p->B_lo, (void *)p->sftA, (void *)p->sftB, (void *)p->stat, (void *)p->maxes})
+    for (void *q : {(void *)p->A_lo, (void *)p->B_lo, (void *)p->C_mid, (void *)p->sftA, (void *)p->sftB, (void *)p->stat, (void *)p->maxes})
         if (q) cudaFree(q);
     if (p->comm)
         for (int o = 0; o < p->comm->world; ++o)
@@ -169,7 +171,7 @@ static int comm_exchange_host(MgComm &c, const void *mine, size_t bytes, void *a
 }
 
 static int plan_create(MgPlan **out, MgComm *c, int dtype, int opA, int opB, size_t m, size_t n, size_t k_local, unsigned N, int fast) {
-    if (!out || !c || !c->connected || (dtype != F32 && dtype != F64) || opA < 0 || opA > 2 || opB < 0 || opB > 2) return G8_STATUS_INVALID_VALUE;
+    if (!out || !c || !c->connected || dtype < F32 || dtype > C64 || opA < 0 || opA > 2 || opB < 0 || opB > 2) return G8_STATUS_INVALID_VALUE;
     if (N < 2 || N > G8_MAX_MODULI || m == 0 || n == 0 || k_local == 0) return G8_STATUS_INVALID_VALUE;
     const size_t W = (size_t)c->world;
     if (n % W || (n / W) % 256) return G8_STATUS_INVALID_VALUE;              // the scatter hands whole 256-column tiles to one owner
@@ -180,6 +182,7 @@ static int plan_create(MgPlan **out, MgComm *c, int dtype, int opA, int opB, siz
     p->comm = c, p->dtype = dtype, p->opA = opA, p->opB = opB, p->fast = fast, p->m = m, p->n = n, p->k = k_local, p->N = N;
     p->m_pad = pad256(m), p->k_pad = pad256(k_local), p->n_pad = pad256(n), p->nc = n / W;
     p->sizeA = p->k_pad * p->m_pad, p->sizeB = p->k_pad * n;
+    p->cplx = dtype >= C32, p->sets = p->cplx ? 3 : 1, p->bsets = p->cplx ? 2 : 1;
     if ((m + n) * sizeof(double) > c->slot_bytes || (p->m_pad + p->n_pad) * sizeof(int32_t) > c->slot_bytes) {
         delete p;
         return G8_STATUS_NOT_SUPPORTED; // mailbox slots too small for this problem: create the communicator with a larger max_vector_bytes
@@ -190,8 +193,9 @@ static int plan_create(MgPlan **out, MgComm *c, int dtype, int opA, int opB, siz
     };
 #define G8_ALLOC(ptr, bytes) \
     if (cudaMalloc(reinterpret_cast<void **>(&(ptr)), (bytes)) != cudaSuccess) return fail((int)cudaErrorMemoryAllocation)
-    G8_ALLOC(p->A_lo, p->sizeA * N);
-    G8_ALLOC(p->B_lo, p->sizeB * N);
+    G8_ALLOC(p->A_lo, p->sizeA * N * p->sets);
+    G8_ALLOC(p->B_lo, p->sizeB * N * p->sets);
+    if (p->cplx) G8_ALLOC(p->C_mid, 2 * (size_t)N * p->nc * p->m_pad);
     G8_ALLOC(p->sftA, sizeof(int16_t) * p->m_pad);
     G8_ALLOC(p->sftB, sizeof(int16_t) * p->n_pad);
     G8_ALLOC(p->stat, sizeof(double) * 4 * (m + n));
@@ -201,10 +205,10 @@ static int plan_create(MgPlan **out, MgComm *c, int dtype, int opA, int opB, siz
     if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess)
         return fail((int)cudaErrorUnknown);
-    const size_t per = (size_t)N * n * p->m_pad; // W shards x N moduli x nc columns x m_pad rows (int8)
+    const size_t per = p->sets * (size_t)N * n * p->m_pad; // W shards x (N moduli [x 3 products]) x nc columns x m_pad rows (int8)
     p->abar_off   = per;
-    p->bbar_off   = per + W * p->sizeA;
-    p->recv_bytes = per + (fast ? 0 : W * p->sizeA + W * p->nc * p->k_pad);
+    p->bbar_off   = per + W * p->bsets * p->sizeA;
+    p->recv_bytes = per + (fast ? 0 : W * p->bsets * (p->sizeA + p->nc * p->k_pad));
     unsigned char handle[64];
     if (int e = g8_peer_alloc(p->recv_bytes, reinterpret_cast<void **>(&p->recv), handle)) return fail(e);
     std::vector<unsigned char> all(64 * W);
@@ -263,21 +267,33 @@ static int run(MgPlan &p, const void *alpha, const void *A, size_t lda, const vo
         G8_TRY(g8_stage_split(p.dtype, 1, p.opA, m, k, A, lda, N, 3, p.sftA, p.A_lo, p.sizeA, N, pst));
         G8_TRY(g8_stage_shift_from_stats(amax_r + m, nullptr, n, N, 1, p.sftB, psd));
         G8_TRY(g8_stage_split(p.dtype, 0, p.opB, n, k, B, ldb, N, 3, p.sftB, p.B_lo, p.sizeB, N, psd));
-        const size_t bslab = nc * p.k_pad;
+        // gathered layout: A-bar [slab][|Re| (,|Im|)][m_pad][k_pad], B-bar [slab][|Re| (,|Im|)][nc][k_pad]
+        const size_t bslab = nc * p.k_pad, bs = p.bsets;
         for (size_t j = 0; j < W; ++j) { // A-bar travels while the B-bar kernel still runs on the helper stream
             const size_t o = ((size_t)c.rank + j) % W; // staggered targets
-            G8_TRY(cudaMemcpyAsync(p.peer_recv[o] + p.abar_off + (size_t)c.rank * p.sizeA, p.A_lo, p.sizeA, cudaMemcpyDefault, st));
+            G8_TRY(cudaMemcpyAsync(p.peer_recv[o] + p.abar_off + (size_t)c.rank * bs * p.sizeA, p.A_lo, bs * p.sizeA, cudaMemcpyDefault, st));
         }
         G8_TRY(join());
         for (size_t j = 0; j < W; ++j) {
             const size_t o = ((size_t)c.rank + j) % W;
-            G8_TRY(cudaMemcpyAsync(p.peer_recv[o] + p.bbar_off + (size_t)c.rank * bslab, p.B_lo + o * bslab, bslab, cudaMemcpyDefault, st));
+            for (size_t g = 0; g < bs; ++g)
+                G8_TRY(cudaMemcpyAsync(p.peer_recv[o] + p.bbar_off + ((size_t)c.rank * bs + g) * bslab, p.B_lo + g * p.sizeB + o * bslab, bslab, cudaMemcpyDefault, st));
         }
         G8_TRY(comm_barrier(c, st));
         int32_t *mx = p.maxes, *mx_r = p.maxes + (p.m_pad + p.n_pad);
         G8_TRY(cudaMemsetAsync(mx, 0, sizeof(int32_t) * (p.m_pad + p.n_pad), st));
-        G8_TRY(g8_stage_gemm_bound_chain(reinterpret_cast<const int8_t *>(p.recv + p.abar_off), p.sizeA, reinterpret_cast<const int8_t *>(p.recv + p.bbar_off), bslab, m,
-                                         nc, p.k_pad, (int)W, mx, mx + p.m_pad + (size_t)c.rank * nc, pst));
+        if (!p.cplx) {
+            G8_TRY(g8_stage_gemm_bound_chain(reinterpret_cast<const int8_t *>(p.recv + p.abar_off), p.sizeA, reinterpret_cast<const int8_t *>(p.recv + p.bbar_off), bslab,
+                                             m, nc, p.k_pad, (int)W, mx, mx + p.m_pad + (size_t)c.rank * nc, pst));
+        } else {
+            GemmArgs g{};
+            g.A = reinterpret_cast<const int8_t *>(p.recv + p.abar_off), g.B = reinterpret_cast<const int8_t *>(p.recv + p.bbar_off);
+            g.strideA = p.sizeA, g.strideB = bslab, g.m = m, g.n = nc, g.m_pad = mp, g.k_pad = p.k_pad;
+            g.num_units = 1, g.first_modulus = 0, g.epi = EPI_BOUND_MAX_CPLX, g.kchain = (int)W, g.k_true = (int)p.k_pad;
+            g.groupA[0] = 0, g.groupA[1] = 1, g.groupA[2] = 2, g.groupB[0] = 0, g.groupB[1] = 1, g.groupB[2] = 2;
+            g.ldc = mp, g.rowmax = mx, g.colmax = mx + p.m_pad + (size_t)c.rank * nc;
+            G8_TRY(launch_gemm_tc(g, st));
+        }
         G8_TRY((comm_allreduce<int32_t, 0>(c, mx, mx_r, p.m_pad + p.n_pad, st)));
         G8_TRY(fork());
         G8_TRY(g8_stage_finalize_shift(p.sftA, mx_r, m, N, pst));
@@ -288,13 +304,26 @@ static int run(MgPlan &p, const void *alpha, const void *A, size_t lda, const vo
     G8_TRY(g8_stage_split(p.dtype, 1, p.opA, m, k, A, lda, N, 0, p.sftA, p.A_lo, p.sizeA, N, pst));
     G8_TRY(g8_stage_split(p.dtype, 0, p.opB, n, k, B, ldb, N, 0, p.sftB, p.B_lo, p.sizeB, N, psd));
     G8_TRY(join());
+    const size_t units = p.sets * (size_t)N; // real: one product per modulus; complex: the three 3M products per modulus
     {
-        void *tbl[G8_MAX_PEERS];
-        for (size_t o = 0; o < W; ++o) tbl[o] = p.peer_recv[o] + (size_t)c.rank * N * nc * mp;
-        G8_TRY(g8_stage_gemm_scatter(0 /*residues mod p*/, p.A_lo, p.sizeA, p.B_lo, p.sizeB, m, n, p.k_pad, (int)N, 0, tbl, (int)W, c.rank, nc * mp, mp, pst));
+        GemmArgs g{};
+        g.A = p.A_lo, g.B = p.B_lo, g.strideA = p.sizeA, g.strideB = p.sizeB, g.m = m, g.n = n, g.m_pad = mp, g.k_pad = p.k_pad;
+        g.num_units = (int)units, g.first_modulus = 0, g.epi = EPI_MOD_I8, g.k_true = (int)p.k_pad;
+        g.prods = p.cplx ? 3 : 1;
+        for (int i = 0; i < 3; ++i) g.groupA[i] = g.groupB[i] = p.cplx ? i * (int)N : 0; // plane sets Re / Im / Re+Im, N planes each
+        g.out = nullptr, g.out_stride = nc * mp, g.ldc = mp;
+        for (size_t o = 0; o < W; ++o) g.peer_out[o] = p.peer_recv[o] + (size_t)c.rank * units * nc * mp;
+        g.owner_cols = nc, g.rank = c.rank, g.world = (int)W;
+        G8_TRY(launch_gemm_tc(g, st));
     }
     G8_TRY(comm_barrier(c, st)); // every rank's tiles have landed (kernel completion + system-scope release / acquire)
-    G8_TRY(g8_stage_crt_parts(p.dtype, p.recv, (int)W, (size_t)N * nc * mp, mp, nc * mp, m, nc, N, C, ldc, p.sftA, p.sftB + (size_t)c.rank * nc, alpha, beta, pst));
+    if (!p.cplx) {
+        G8_TRY(g8_stage_crt_parts(p.dtype, p.recv, (int)W, (size_t)N * nc * mp, mp, nc * mp, m, nc, N, C, ldc, p.sftA, p.sftB + (size_t)c.rank * nc, alpha, beta, pst));
+    } else {
+        // owner side, complex: sum the shards per 3M product, reduce, recombine {Re, Im} mod p, then the ordinary complex CRT
+        launch_i8_cplx_combine_parts(reinterpret_cast<const int8_t *>(p.recv), (int)W, units * nc * mp, nc * mp, (int)N, 0, p.C_mid, nc * mp, st);
+        G8_TRY(g8_stage_crt(p.dtype, p.C_mid, mp, nc * mp, m, nc, N, C, ldc, p.sftA, p.sftB + (size_t)c.rank * nc, alpha, beta, pst));
+    }
     // (the next call's first all-reduce orders every rank's CRT before anybody's next scatter into the receive areas)
     return (int)cudaPeekAtLastError();
 }

@@ -443,8 +443,8 @@ class NativeKShardGemm:
 
     def __init__(self, m, n, k_local, num_moduli, fastmode=False, dtype=torch.float64, device=None, group=None, op_A="N", op_B="N"):
         from . import _lib
-        if dtype not in (torch.float32, torch.float64):
-            raise NotImplementedError("K-sharded path: real S/D GEMM only")
+        if dtype not in api._DTYPES:
+            raise NotImplementedError("K-sharded path: S/D/C/Z GEMM (INT8 backend)")
         self.lib, self.group = _lib.load(), group
         self.W, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.m, self.n, self.k, self.N, self.dtype = m, n, k_local, num_moduli, dtype

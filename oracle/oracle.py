@@ -11,8 +11,8 @@ this module.  It restates the reference's INT8 Ozaki-II pipeline stage by stage
 
 Parity pin: `tests/test_oracle.py` checks it against the reference's known-answer vector
 (sample/dgemm_cuBLASLt_int8.cu:26-40 -> tests/golden/sample_kat.json) and a pure-Python big-integer
-model; on the GPU box `tests/test_parity_ref.py` checks the CUDA path against the unmodified
-reference library itself (oracle/_ref/libgemmul8_ref.so).  The device's __log2f cannot be reproduced
+model; on the GPU box `tests/test_gpu_ref_parity.py`, `tests/test_gpu_configs.py` and `tests/test_gpu_skip_scaling.py` check the CUDA
+path against the unmodified reference library itself (oracle/_ref/libgemmul8_ref.so).  The device's __log2f cannot be reproduced
 on a CPU, so shift exponents may be passed in (from the device) and are otherwise computed with an
 exact log2 plus an `ambiguous` mask for rows that sit on a floor() boundary.
 """

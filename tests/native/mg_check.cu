@@ -6,6 +6,7 @@
 //   usage: mg_check [world]      (default: all visible GPUs, at most 8; needs >= 2)
 #include "../../include/gemmul8_c.h"
 
+#include <cuComplex.h>
 #include <cuda_runtime.h>
 #include <sys/mman.h>
 #include <sys/wait.h>
@@ -54,9 +55,13 @@ template <typename T> static int run_case(g8_mg_comm *comm, int rank, int world,
     else { CK(cudaMemcpy2D(Al, sizeof(T) * kl, A + (size_t)rank * kl, sizeof(T) * K, sizeof(T) * kl, m, cudaMemcpyDeviceToDevice)); } // rows K_r
     if (opB == G8_OP_N) { CK(cudaMemcpy2D(Bl, sizeof(T) * kl, B + (size_t)rank * kl, sizeof(T) * K, sizeof(T) * kl, n, cudaMemcpyDeviceToDevice)); } // rows K_r
     else { CK(cudaMemcpy(Bl, B + (size_t)rank * kl * n, sizeof(T) * n * kl, cudaMemcpyDeviceToDevice)); } // columns K_r
-    const T one = 1, zero = 0;
+    T one, zero;
+    std::memset(&one, 0, sizeof(T)), std::memset(&zero, 0, sizeof(T));
+    if (dtype == G8_R32F || dtype == G8_C32F) *reinterpret_cast<float *>(&one) = 1.0f;
+    else *reinterpret_cast<double *>(&one) = 1.0;
+    const bool cplx = dtype >= G8_C32F;
     // single-GPU reference on the full K
-    const size_t wbytes = g8_work_size(0, G8_BACKEND_INT8, m, n, K, N, 0, 0, nullptr, nullptr);
+    const size_t wbytes = g8_work_size(cplx, G8_BACKEND_INT8, m, n, K, N, 0, 0, nullptr, nullptr);
     void *work;
     CK(cudaMalloc(&work, wbytes));
     g8_gemm_desc d{};
@@ -74,9 +79,15 @@ template <typename T> static int run_case(g8_mg_comm *comm, int rank, int world,
     CK(cudaMemcpy(got.data(), Cslab, sizeof(T) * m * nc, cudaMemcpyDeviceToHost));
     const bool same = std::memcmp(want.data(), got.data(), sizeof(T) * m * nc) == 0;
     double num = 0, den = 0;
-    for (size_t i = 0; i < m * nc; ++i) num = std::fmax(num, std::fabs((double)want[i] - (double)got[i])), den = std::fmax(den, std::fabs((double)want[i]));
-    const bool ok = fast ? (num <= (sizeof(T) == 8 ? 1e-9 : 1e-3) * den) : same;
-    std::printf("rank %d: %cGEMM N=%u %s op%d%d  %s (max diff / max = %.2e)\n", rank, sizeof(T) == 8 ? 'D' : 'S', N, fast ? "fast" : "accu", opA, opB,
+    const bool dbl = dtype == G8_R64F || dtype == G8_C64F;
+    const size_t scalars = m * nc * (cplx ? 2 : 1);
+    for (size_t i = 0; i < scalars; ++i) {
+        const double w = dbl ? reinterpret_cast<const double *>(want.data())[i] : (double)reinterpret_cast<const float *>(want.data())[i];
+        const double g = dbl ? reinterpret_cast<const double *>(got.data())[i] : (double)reinterpret_cast<const float *>(got.data())[i];
+        num = std::fmax(num, std::fabs(w - g)), den = std::fmax(den, std::fabs(w));
+    }
+    const bool ok = fast ? (num <= (dbl ? 1e-9 : 1e-3) * den) : same;
+    std::printf("rank %d: %cGEMM N=%u %s op%d%d  %s (max diff / max = %.2e)\n", rank, "SDCZ"[dtype], N, fast ? "fast" : "accu", opA, opB,
                 same ? "bit-identical" : (ok ? "within tolerance" : "MISMATCH"), den > 0 ? num / den : 0.0);
     CK(g8_mg_plan_destroy(plan));
     cudaFree(A), cudaFree(B), cudaFree(Cfull), cudaFree(Cslab), cudaFree(Al), cudaFree(Bl), cudaFree(work);
@@ -95,6 +106,8 @@ static int rank_main(Shared *sh, int rank, int world) {
         bad += run_case<double>(comm, rank, world, G8_R64F, 14, fast, G8_OP_N, G8_OP_N);
         bad += run_case<double>(comm, rank, world, G8_R64F, 15, fast, G8_OP_T, G8_OP_T);
         bad += run_case<float>(comm, rank, world, G8_R32F, 6, fast, G8_OP_N, G8_OP_T);
+        bad += run_case<cuDoubleComplex>(comm, rank, world, G8_C64F, 10, fast, G8_OP_N, G8_OP_N);
+        bad += run_case<cuFloatComplex>(comm, rank, world, G8_C32F, 6, fast, G8_OP_C, G8_OP_T);
     }
     CK(g8_mg_comm_barrier(comm, nullptr));
     CK(cudaDeviceSynchronize());

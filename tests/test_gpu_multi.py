@@ -38,7 +38,7 @@ def _worker(rank, world, port, q):
         from gemmul8_b200 import multi_gpu
 
         ok_all = True
-        for dtype, N in ((torch.float64, 14), (torch.float32, 6)):
+        for dtype, N in ((torch.float64, 14), (torch.float32, 6), (torch.complex128, 10), (torch.complex64, 6)):
             m, n, kl = 300, 256 * world, 384   # n / world = 256: one scatter tile per owner
             K = kl * world
             # full operands (same on every rank), column-major
@@ -58,6 +58,8 @@ def _worker(rank, world, port, q):
                         if world <= 4:
                             continue
                         variant = "fused"
+                    if dtype.is_complex and variant != "native":
+                        continue   # complex K-shards: the native driver (3M product units + owner-side recombination)
                     plan = (multi_gpu.NativeKShardGemm(m, n, kl, N, fastmode=fast, dtype=dtype, device=f"cuda:{rank}") if variant == "native" else
                             multi_gpu.KShardGemm(m, n, kl, N, fastmode=fast, dtype=dtype, device=f"cuda:{rank}", variant=variant))
                     C = torch.zeros(plan.local_out_elems, dtype=dtype, device=f"cuda:{rank}")
@@ -70,7 +72,7 @@ def _worker(rank, world, port, q):
                     if not fast:
                         ok = torch.equal(C, want)          # accurate mode: bit-identical to the single-GPU call
                     else:
-                        ok = bool(((C - want).abs().max() / want.abs().max()) < (1e-9 if dtype == torch.float64 else 1e-3))
+                        ok = bool(((C - want).abs().max() / want.abs().max()) < (1e-9 if dtype in (torch.float64, torch.complex128) else 1e-3))
                     ok_all &= ok
                     if not ok:
                         print(f"rank {rank} mismatch dtype={dtype} fast={fast} variant={variant}", flush=True)

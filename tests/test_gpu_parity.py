@@ -410,3 +410,68 @@ def test_fp8_tensor_core_accumulation_is_exact(env):
     r = subprocess.run([sys.executable, str(ROOT / "tools" / "f8_probe.py")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
     assert "F8 EXACT" in r.stdout and "NOT EXACT" not in r.stdout, r.stdout[-1500:]
+
+
+@pytest.mark.parametrize("dtype,N", [(np.float64, 14), (np.float32, 6), (np.complex128, 10), (np.complex64, 6)])
+@pytest.mark.parametrize("fast", [False, True])
+def test_native_kshard_driver_world1_matches_gemm(env, dtype, N, fast):
+    """The native multi-GPU driver (g8_mg_comm_* / g8_mg_plan_* / g8_gemm_mg, csrc/g8_mg.cu) with a world of ONE rank: the whole path --
+    mailbox all-reduce, flag barrier, bound-plane exchange + chained bound GEMM, GEMM -> scatter, owner-side shard sum (+ complex 3M
+    recombination) + CRT -- runs on a single GPU and must reproduce g8_gemm: accurate mode bit for bit, fast mode to the documented
+    tolerance (its statistics kernels differ).  (2 - 8 ranks: tests/test_gpu_multi.py and tests/native/mg_check.cu.)"""
+    import ctypes
+    torch, H = env.torch, env.H
+    from gemmul8_b200 import _lib, api
+
+    lib = _lib.load()
+    rng = np.random.default_rng(31)
+    m, n, k = 200, 512, 700
+    cplx = np.dtype(dtype).kind == "c"
+    tdt = H.NP2T[np.dtype(dtype)]
+    for opA, opB in (("N", "N"), ("T", "C" if cplx else "T")):
+        A = H.rand_matrix(rng, H.stored_shape(opA, m, k), dtype)
+        B = H.rand_matrix(rng, H.stored_shape(opB, k, n), dtype)
+        want = H.run_gemm(A, B, opA, opB, N, fast)
+        dA, lda = H.to_dev_colmajor(A)
+        dB, ldb = H.to_dev_colmajor(B)
+        dC, ldc = H.to_dev_colmajor(np.zeros((m, n), dtype=dtype))
+        comm, plan = ctypes.c_void_p(), ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        api._check(lib.g8_mg_comm_create(ctypes.byref(comm), 1, 0, 8 * (m + n) + 4096, handle), "comm_create")
+        api._check(lib.g8_mg_comm_connect(comm, handle), "comm_connect")
+        api._check(lib.g8_mg_plan_create(ctypes.byref(plan), comm, api._DTYPES[tdt], api._op(opA), api._op(opB), m, n, k, N, int(fast)), "plan_create")
+        keep = []
+        pa, pb = api._scalar_ptr(1.0, tdt, keep), api._scalar_ptr(0.0, tdt, keep)
+        for _ in range(2):
+            api._check(lib.g8_gemm_mg(plan, pa, dA.data_ptr(), lda, dB.data_ptr(), ldb, pb, dC.data_ptr(), ldc, torch.cuda.current_stream().cuda_stream), "gemm_mg")
+        torch.cuda.synchronize()
+        assert lib.g8_mg_comm_status(comm) == 0
+        got = H.from_dev_colmajor(dC, m, n, ldc)
+        lib.g8_mg_plan_destroy(plan)
+        lib.g8_mg_comm_destroy(comm)
+        if not fast:
+            assert H.bits_equal(got, want), H.first_diff(got, want, f"C {opA}{opB}")
+        else:
+            assert np.abs(got - want).max() <= (1e-9 if np.dtype(dtype).itemsize >= 8 and np.dtype(dtype) != np.dtype(np.complex64) else 1e-3) * np.abs(want).max()
+
+
+def test_bound_gemm_chained_over_kslabs(env):
+    """g8_stage_gemm_bound_chain: one accumulator sums the products of `chain` gathered K-slabs; row / column maxima vs numpy"""
+    import ctypes
+    torch = env.torch
+    from gemmul8_b200 import _lib, api
+
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    m, n, kp, chain = 300, 200, 512, 3
+    mp = api.pad256(m)
+    A = rng.integers(0, 65, size=(chain, mp, kp)).astype(np.int8)
+    B = rng.integers(0, 65, size=(chain, n, kp)).astype(np.int8)
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    rowmax = torch.zeros(mp, dtype=torch.int32, device="cuda")
+    colmax = torch.zeros(api.pad256(n), dtype=torch.int32, device="cuda")
+    api._check(lib.g8_stage_gemm_bound_chain(dA.data_ptr(), mp * kp, dB.data_ptr(), n * kp, m, n, kp, chain, rowmax.data_ptr(), colmax.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream), "bound_chain")
+    torch.cuda.synchronize()
+    Hs = sum(A[c, :m].astype(np.int64) @ B[c].astype(np.int64).T for c in range(chain))
+    assert np.array_equal(rowmax.cpu().numpy()[:m], Hs.max(axis=1)) and np.array_equal(colmax.cpu().numpy()[:n], Hs.max(axis=0))

@@ -342,9 +342,13 @@ def check_ref():
                     dA_ = np.abs(W["sftA"].astype(int) - Wr["sftA"].astype(int)).max()
                     dB_ = np.abs(W["sftB"].astype(int) - Wr["sftB"].astype(int)).max()
                     scale = np.abs(Cr).max()
-                    # a one-step shift difference changes the truncation of one operand: results agree to the EMULATED precision,
-                    # ~2^-(log2P - O(log k)) (each operand keeps about log2P bits), capped below by the type's epsilon
-                    tol = max(8 * np.finfo(np.dtype(dtype)).eps, 2.0 ** (-T.log2P("FP8", N) + 10))
+                    # a one-step shift difference changes the truncation of one operand: the two results then agree to the EMULATED
+                    # precision, measured here as the reference's own error against the exact (float64 / complex128) product; 4x that
+                    # (>= 2 ulp of the type).  tools/fp8_shift_stats.py: at DGEMM 8192^3, N = 8 .. 20, phi in {-1, 1} NO shift differed.
+                    wide = np.complex128 if cplx else np.float64
+                    opx = {"N": A, "T": A.T, "C": A.conj().T}[opA].astype(wide) @ {"N": B, "T": B.T, "C": B.conj().T}[opB].astype(wide)
+                    err_ref = np.abs(Cr - opx).max() / scale
+                    tol = 4 * max(err_ref, 2 * np.finfo(np.dtype(dtype)).eps)
                     ok_tol = dA_ <= 1 and dB_ <= 1 and np.abs(C - Cr).max() <= tol * scale
                     report(f"ref-parity(fp8 accu, tol) {np.dtype(dtype).name} N={N} {m}x{n}x{k} {opA}{opB}", code == 0 and ok_tol,
                            f"dsft=({dA_},{dB_}) maxdiff/scale={np.abs(C - Cr).max() / scale:.2e}")
