@@ -141,7 +141,11 @@ int main(int argc, char **argv) {
     std::vector<pid_t> pids;
     for (int r = 0; r < world; ++r) {
         const pid_t p = fork();
-        if (p == 0) _exit(rank_main(sh, r, world) ? 1 : 0);
+        if (p == 0) {
+            const int rc = rank_main(sh, r, world) ? 1 : 0;
+            std::fflush(stdout), std::fflush(stderr); // _exit does not flush stdio
+            _exit(rc);
+        }
         pids.push_back(p);
     }
     int bad = 0;
