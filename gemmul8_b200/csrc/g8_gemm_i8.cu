@@ -65,6 +65,28 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
                  ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+// the same loads with an L2 eviction-priority hint (createpolicy): the band operand that is re-used across a whole sweep is kept
+// (evict_last), the streamed panels / the output must not displace it
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_3d_hint(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm_hint(void *smem_dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1, int c2, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -271,6 +293,7 @@ struct KParams {
     void *peer_out[G8_MAX_PEERS];
     int owner_cols;
     int prods, set_stride; // EPI_F8_PROD
+    int l2hint; // bit 0: evict_last for the band (lane-side) operand loads; bit 1: evict_first for the column-side panels; bit 2: streaming C_mid stores
     int kchain; // EPI_BOUND_MAX only: the accumulator sums `kchain` plane pairs (plane c of both operands = K-slab c of a K-sharded bound product)
     int group;  // lane tiles per rasterisation band (tile_coord)
     int tl_rot; // rotation of the lane-tile sweep so that the ranks do not all target the same owner at the same time
@@ -347,6 +370,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            const uint64_t polL = l2_policy_evict_last(), polC = l2_policy_evict_first();
+            const bool hintL = P.l2hint & 1, hintC = P.l2hint & 2;
             for (int t = cid; t < total_tiles; t += ncl) {
                 const TileCoord tc = tile_coord(t, P.tiles_l, P.tiles_c, P.tl_rot, P.group);
                 const int nchain = (EPI == EPI_BOUND_MAX) ? P.kchain : (EPI == EPI_BOUND_MAX_CPLX) ? 2 * P.kchain : EC::NCHAIN;
@@ -391,12 +416,17 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                                 // both CTAs load their share; all bytes complete on the leader's barrier
                                 if (leader) mbar_expect_tx(&full_bar[stage], KS::STAGE * 2);
                                 const uint32_t lbar = mapa(smem_u32(&full_bar[stage]), 0);
-                                tma_load_3d_2sm(sL, &mapL, lbar, kb * BLOCK_K, tc.tl * (TILE_LANE * 2) + (int)rank * TILE_LANE, planeB);
-                                tma_load_3d_2sm(sC, &mapC, lbar, kb * BLOCK_K, tc.tc * TILE_COL + (int)rank * (TILE_COL / 2), planeA);
+                                const int cl = tc.tl * (TILE_LANE * 2) + (int)rank * TILE_LANE, cc = tc.tc * TILE_COL + (int)rank * (TILE_COL / 2);
+                                if (hintL) tma_load_3d_2sm_hint(sL, &mapL, lbar, kb * BLOCK_K, cl, planeB, polL);
+                                else tma_load_3d_2sm(sL, &mapL, lbar, kb * BLOCK_K, cl, planeB);
+                                if (hintC) tma_load_3d_2sm_hint(sC, &mapC, lbar, kb * BLOCK_K, cc, planeA, polC);
+                                else tma_load_3d_2sm(sC, &mapC, lbar, kb * BLOCK_K, cc, planeA);
                             } else {
                                 mbar_expect_tx(&full_bar[stage], KS::STAGE);
-                                tma_load_3d(sL, &mapL, &full_bar[stage], kb * BLOCK_K, tc.tl * TILE_LANE, planeB);
-                                tma_load_3d(sC, &mapC, &full_bar[stage], kb * BLOCK_K, tc.tc * TILE_COL, planeA);
+                                if (hintL) tma_load_3d_hint(sL, &mapL, &full_bar[stage], kb * BLOCK_K, tc.tl * TILE_LANE, planeB, polL);
+                                else tma_load_3d(sL, &mapL, &full_bar[stage], kb * BLOCK_K, tc.tl * TILE_LANE, planeB);
+                                if (hintC) tma_load_3d_hint(sC, &mapC, &full_bar[stage], kb * BLOCK_K, tc.tc * TILE_COL, planeA, polC);
+                                else tma_load_3d(sC, &mapC, &full_bar[stage], kb * BLOCK_K, tc.tc * TILE_COL, planeA);
                             }
                             if (++stage == NUM_STAGES) stage = 0, phase ^= 1;
                         }
@@ -495,8 +525,13 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                         w[j] = (uint32_t)(r0 & 0xFF) | ((uint32_t)(r1 & 0xFF) << 8) | ((uint32_t)(r2 & 0xFF) << 16) | ((uint32_t)r3 << 24);
                     }
                     if (col_ok) {
-                        *reinterpret_cast<uint4 *>(dst + c0)      = make_uint4(w[0], w[1], w[2], w[3]);
-                        *reinterpret_cast<uint4 *>(dst + c0 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+                        if (P.l2hint & 4) { // C_mid is written once and read much later (CRT): do not let it displace the operand band
+                            __stcs(reinterpret_cast<uint4 *>(dst + c0), make_uint4(w[0], w[1], w[2], w[3]));
+                            __stcs(reinterpret_cast<uint4 *>(dst + c0 + 16), make_uint4(w[4], w[5], w[6], w[7]));
+                        } else {
+                            *reinterpret_cast<uint4 *>(dst + c0)      = make_uint4(w[0], w[1], w[2], w[3]);
+                            *reinterpret_cast<uint4 *>(dst + c0 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+                        }
                     }
                 }
             } else if constexpr (EPI == EPI_MOD_I8_SCATTER) {
@@ -853,6 +888,8 @@ template <int EPI, int CG> static int launch_tc_cg(const GemmArgs &g, cudaStream
     P.inflate = (float)(g.k_true + 1) * 0x1p-24f;
     P.owner_cols = 0, P.tl_rot = 0;
     P.kchain = g.kchain > 0 ? g.kchain : 1;
+    static const int l2hint_pref = [] { const char *e = getenv("G8_GEMM_L2HINT"); return e ? atoi(e) : 4; }(); // default: streaming C_mid stores (r02h)
+    P.l2hint = l2hint_pref;
     static const int group_pref = [] { const char *e = getenv("G8_GEMM_GROUP"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 16; }();
     P.group = group_pref;
     P.prods = g.prods > 0 ? g.prods : (EPI == EPI_F8_PROD ? 3 : 1), P.set_stride = g.set_stride;
