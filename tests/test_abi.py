@@ -75,3 +75,34 @@ def test_cxx_and_hook_symbols_match_reference():
     have = set(re.findall(r" T (\S+)", out))
     assert len(want) == 16 and set(want) <= have
     assert {"cublasSgemm_v2", "cublasDgemm_v2", "cublasCgemm_v2", "cublasZgemm_v2", "cublasGemmEx", "cublasDestroy_v2"} <= have
+
+
+def test_argument_validation_needs_no_gpu():
+    """Argument errors are reported before the device is touched: the k limits of both backends (2^17 INT8; 2^16 FP8, where binary32
+    accumulation of the piece products stops being exact -- ADVICE r01), and the plan / communicator constructors of the host-buffer
+    and multi-GPU entry points."""
+    lib = _lib.load()
+    INVALID = 10001
+    d = _lib.GemmDesc()
+    buf = (ctypes.c_double * 64)()
+    p = ctypes.addressof(buf)
+    d.A = d.B = d.C = d.alpha = d.beta = d.work = p
+    d.dtype, d.m, d.n, d.num_moduli = 1, 4, 4, 14
+    d.backend, d.k = 0, (1 << 17) + 1
+    assert lib.g8_gemm(ctypes.byref(d), None) == INVALID
+    d.backend, d.k = 1, (1 << 16) + 1
+    assert lib.g8_gemm(ctypes.byref(d), None) == INVALID
+    plan = ctypes.c_void_p()
+    assert lib.g8_host_plan_create(ctypes.byref(plan), 7, 0, 0, 0, 8, 8, 8, 14, 0, 0) == INVALID          # dtype
+    assert lib.g8_host_plan_create(ctypes.byref(plan), 1, 0, 0, 3, 8, 8, 8, 14, 0, 0) == INVALID          # op_B
+    assert lib.g8_host_plan_create(ctypes.byref(plan), 1, 1, 0, 0, 8, 8, (1 << 16) + 1, 8, 0, 0) == INVALID   # FP8 k limit
+    assert lib.g8_host_plan_create(ctypes.byref(plan), 1, 0, 0, 0, 8, 8, 8, 21, 0, 0) == INVALID          # num_moduli
+    assert lib.g8_gemm_host(None, p, p, 8, p, 8, p, p, 8, None) == INVALID
+    comm = ctypes.c_void_p()
+    handle = ctypes.create_string_buffer(64)
+    assert lib.g8_mg_comm_create(ctypes.byref(comm), 0, 0, 4096, handle) == INVALID
+    assert lib.g8_mg_comm_create(ctypes.byref(comm), 9, 0, 4096, handle) == INVALID                       # more than the 8 GPUs of a box
+    assert lib.g8_mg_comm_create(ctypes.byref(comm), 2, 2, 4096, handle) == INVALID                       # rank out of range
+    assert lib.g8_mg_plan_create(ctypes.byref(plan), None, 1, 0, 0, 256, 256, 256, 14, 0) == INVALID
+    assert lib.g8_gemm_mg(None, p, p, 8, p, 8, p, p, 8, None) == INVALID
+    assert lib.g8_stage_gemm_bound_chain(p, 256, p, 256, 8, 8, 256, 0, p, p, None) != 0                   # chain < 1 (or no device)
