@@ -601,6 +601,7 @@ __attribute__((visibility("default"))) int g8_stage_split(int dtype, int is_A, i
     if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
     if (!X || !sft || !planes || dtype < F32 || dtype > C64 || num_moduli < 2 || num_moduli > G8_MAX_MODULI) return G8_STATUS_INVALID_VALUE;
     if (rows == 0 || k == 0) return 0;
+    if (k > (size_t(1) << 17)) return G8_STATUS_INVALID_VALUE; // same bound as g8_gemm (include/gemmul8.hpp:29)
     SplitArgs a = split_args(is_A, op, rows, k, X, ld, num_moduli, sft, planes, plane_stride_bytes, group_stride_planes);
     if (mode >= 2)
         for (int g = 0; g < 3; ++g) a.planes[g] = planes + g * plane_stride_bytes;
@@ -620,6 +621,7 @@ __attribute__((visibility("default"))) int g8_stage_gemm(int epilogue, int use_s
                   size_t ldc, int32_t *rowmax, int32_t *colmax, void *stream) {
     if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
     if (!A_lo || !B_lo || k_pad % 256 || epilogue < 0 || epilogue > 7) return G8_STATUS_INVALID_VALUE;
+    if (k_pad > (size_t(1) << 17)) return G8_STATUS_INVALID_VALUE; // |sum| <= k * 2^14 must fit INT32 (and f32 exactly for the FP8 pieces: callers keep k <= 2^16)
     GemmArgs g{};
     g.A = A_lo, g.B = B_lo, g.strideA = strideA, g.strideB = strideB, g.m = m, g.n = n, g.m_pad = pad256(m), g.k_pad = k_pad;
     g.num_units = num_units, g.first_modulus = first_modulus, g.epi = epilogue;
@@ -718,7 +720,7 @@ __attribute__((visibility("default"))) int g8_stage_gemm_scatter(int epilogue, c
                                                                   size_t k_pad, int num_units, int first_modulus, void *const *peer_out, int world, int rank,
                                                                   size_t out_stride, size_t ldc, void *stream) {
     if (!device_ok()) return G8_STATUS_NO_DEVICE_CODE;
-    if (!A_lo || !B_lo || !peer_out || k_pad % 256 || (epilogue != EPI_MOD_I8 && epilogue != EPI_RAW_I32)) return G8_STATUS_INVALID_VALUE;
+    if (!A_lo || !B_lo || !peer_out || k_pad % 256 || k_pad > (size_t(1) << 17) || (epilogue != EPI_MOD_I8 && epilogue != EPI_RAW_I32)) return G8_STATUS_INVALID_VALUE;
     if (world < 1 || world > G8_MAX_PEERS || rank < 0 || rank >= world || n % (size_t)world || (n / (size_t)world) % 256) return G8_STATUS_INVALID_VALUE;
     GemmArgs g{};
     g.A = A_lo, g.B = B_lo, g.strideA = strideA, g.strideB = strideB, g.m = m, g.n = n, g.m_pad = pad256(m), g.k_pad = k_pad;
