@@ -233,12 +233,17 @@ template <> struct EpiCfg<EPI_MOD_I8_SCATTER> { static constexpr int TILE_COL = 
 template <> struct EpiCfg<EPI_RAW_I32_SCATTER> { static constexpr int TILE_COL = 256, NACC = 1, NCHAIN = 1; };
 template <> struct EpiCfg<EPI_F8_BOUND_CPLX>  { static constexpr int TILE_COL = 128, NACC = 2, NCHAIN = 2; };
 template <> struct EpiCfg<EPI_F8_PROD>        { static constexpr int TILE_COL = 256, NACC = 1, NCHAIN = 1; };
-// EPI_MOD_I8_SCATTER staging: per epilogue warp 32 columns x (SCAT_ROWS + 16 B pad); the pad makes the 16-byte shared stores of
-// the 32 lanes (one column each) bank-conflict free: a (16 mod 128)-byte stride puts lane l at bank 4l mod 32
-#ifndef G8_SCAT_ROWS
-#define G8_SCAT_ROWS 256 // rows per bulk copy: 256-byte segments measured 0-6 % faster than 128 over NVLink (costs one TMA stage: 5 instead of 6)
+// Scatter staging.
+// EPI_MOD_I8_SCATTER: per epilogue warp G8_SCAT_BUFS buffers of 32 columns x 128 rows (4 KB, 128 B per column, 16-byte chunks XOR-swizzled
+// by column & 7 = CU_TENSOR_MAP_SWIZZLE_128B, which also makes the 16-byte shared stores of the 32 lanes conflict-free); ONE TMA tensor
+// store per buffer.  (r02: one 256-byte cp.async.bulk per THREAD -- 256 copy-engine operations per CTA and tile, which cost 10 % of the
+// GEMM even with every receive area on the local GPU; the tensor store needs 8.)
+// EPI_RAW_I32_SCATTER (non-default INT32 bound exchange): per thread one 128-byte bulk copy per TMEM chunk from a padded row.
+#ifndef G8_SCAT_BUFS
+#define G8_SCAT_BUFS 2
 #endif
-constexpr int SCAT_ROWS = G8_SCAT_ROWS, SCAT_PITCH = SCAT_ROWS + 16, SCAT_WARP_BYTES = 32 * SCAT_PITCH, SCAT_BYTES = 4 * SCAT_WARP_BYTES;
+constexpr int SCAT_BUF_BYTES = 32 * 128, SCAT_TMA_WARP_BYTES = G8_SCAT_BUFS * SCAT_BUF_BYTES, SCAT_TMA_BYTES = 4 * SCAT_TMA_WARP_BYTES;
+constexpr int SCAT_PITCH = 128 + 16, SCAT_WARP_BYTES = 32 * SCAT_PITCH, SCAT_BYTES = 4 * SCAT_WARP_BYTES;
 template <int EPI> constexpr bool is_f8 = (EPI == EPI_F8_MOD || EPI == EPI_F8_BOUND || EPI == EPI_F8_RAW || EPI == EPI_F8_BOUND_CPLX || EPI == EPI_F8_PROD);
 
 // CG = 1: one CTA per tile (128 columns of C x TILE_COL rows).  CG = 2: a CTA pair (tcgen05 cta_group::2) shares a
@@ -250,12 +255,13 @@ template <int EPI, int CG = 1> struct KernelShape {
     static constexpr int STAGE_L    = TILE_LANE * BLOCK_K;         // bytes: lane-side operand (B_lo tile), per CTA
     static constexpr int STAGE_C    = TILE_COL / CG * BLOCK_K;     // bytes: column-side operand (A_lo tile), per CTA
     static constexpr int STAGE      = STAGE_L + STAGE_C;
-    static constexpr int SCAT       = (EPI == EPI_MOD_I8_SCATTER || EPI == EPI_RAW_I32_SCATTER) ? SCAT_BYTES : 0; // epilogue staging
+    static constexpr int SCAT       = EPI == EPI_MOD_I8_SCATTER ? SCAT_TMA_BYTES : EPI == EPI_RAW_I32_SCATTER ? SCAT_BYTES : 0; // epilogue staging
+    static constexpr int BARS       = EPI == EPI_MOD_I8_SCATTER ? 1024 : 256; // barrier area (keeps the swizzled staging 1024-byte aligned)
     static constexpr int NUM_STAGES = (220 * 1024 - SCAT) / STAGE > 8 ? 8 : (220 * 1024 - SCAT) / STAGE;
     // TMEM is a ring of accumulator SLOTS of TILE_COL columns; a tile takes NACC consecutive slots.  With more slots than
     // NACC (2 vs 1, 4 vs 3) the MMAs of the next tile start while the epilogue still drains the previous one.
     static constexpr int NUM_BUF    = 512 / TILE_COL;
-    static constexpr int SMEM_BYTES = NUM_STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + SCAT;
+    static constexpr int SMEM_BYTES = NUM_STAGES * STAGE + 1024 /*align*/ + BARS + SCAT;
 };
 
 struct TileCoord {
@@ -314,9 +320,15 @@ template <int EPI> __device__ __forceinline__ void chain_groups(int acc, int c, 
     }
 }
 
+// EPI_MOD_I8_SCATTER: one store tensor map per owner, view {ldc rows (bytes), owner_cols, units} of its receive area
+struct PeerMaps {
+    CUtensorMap m[G8_MAX_PEERS];
+};
+
 template <int EPI, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUtensorMap mapC, const KParams P) {
+gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUtensorMap mapC, const KParams P,
+                  const __grid_constant__ PeerMaps PM) {
     using KS = KernelShape<EPI, CG>;
     using EC = EpiCfg<EPI>;
     constexpr int TILE_COL = KS::TILE_COL, NUM_STAGES = KS::NUM_STAGES, NUM_BUF = KS::NUM_BUF;
@@ -480,6 +492,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
         // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
         const int q = warp & 3;
         int buf = 0;
+        [[maybe_unused]] int scat_buf = 0; // EPI_MOD_I8_SCATTER: staging buffer of this warp the next tensor store leaves from
         uint32_t tphase = 0;
         for (int t = cid; t < total_tiles; t += ncl) {
             const TileCoord tc = tile_coord(t, P.tiles_l, P.tiles_c, P.tl_rot, P.group);
@@ -535,19 +548,23 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                     }
                 }
             } else if constexpr (EPI == EPI_MOD_I8_SCATTER) {
-                // residues -> shared memory (this thread's column, SCAT_ROWS rows at a time) -> ONE cp.async.bulk per thread into
-                // the owner's buffer: NVLink sees full 256-byte writes issued by the copy engine instead of 16-byte stores that
-                // stall the epilogue warps on remote latency.
+                // residues -> swizzled shared staging (32 columns x 128 rows per warp) -> ONE TMA tensor store per warp and 128 rows into
+                // the owner's receive area: NVLink sees 128-byte row segments issued by the copy engine, the epilogue warps never wait
+                // on remote latency, and the SM's copy engine handles 8 store operations per tile instead of 256.
                 const int32_t p = g8d_moduli[INT8][midx], pinv = g8d_pinv32[INT8][midx];
-                int8_t *dst = reinterpret_cast<int8_t *>(out_base) + (size_t)tc.unit * P.out_stride + (size_t)col_o * P.ldc + row0;
-                unsigned char *stg = smem + NUM_STAGES * KS::STAGE + 256 + (warp - 2) * SCAT_WARP_BYTES + lane * SCAT_PITCH;
-                const uint32_t stg_s = smem_u32(stg);
+                const int owner  = (tc.tl * (TILE_LANE * CG)) / P.owner_cols;
+                const int col_w  = col_o - lane; // first of this warp's 32 columns inside the owner's slab
+                unsigned char *stg_w = smem + NUM_STAGES * KS::STAGE + KS::BARS + (warp - 2) * SCAT_TMA_WARP_BYTES;
+                const int sw = (lane & 7) << 4;
 #pragma unroll 1
-                for (int h0 = 0; h0 < TILE_COL; h0 += SCAT_ROWS) {
-                    // the copy engine must have finished READING this thread's staging row (previous half / previous tile)
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                for (int h0 = 0; h0 < TILE_COL; h0 += 128) {
+                    // the copy engine must have finished READING the buffer we are about to overwrite
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(G8_SCAT_BUFS - 1) : "memory");
+                    __syncwarp();
+                    unsigned char *buf_s = stg_w + scat_buf * SCAT_BUF_BYTES;
+                    unsigned char *row_s = buf_s + lane * 128;
 #pragma unroll 1
-                    for (int c0 = 0; c0 < SCAT_ROWS; c0 += 32) {
+                    for (int c0 = 0; c0 < 128; c0 += 32) {
                         int32_t v[32];
                         tmem_ld32(taddr0 + h0 + c0, v);
                         tmem_ld_wait();
@@ -558,13 +575,18 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                             const int32_t r2 = mod_i32(v[4 * j + 2], p, pinv), r3 = mod_i32(v[4 * j + 3], p, pinv);
                             w[j] = (uint32_t)(r0 & 0xFF) | ((uint32_t)(r1 & 0xFF) << 8) | ((uint32_t)(r2 & 0xFF) << 16) | ((uint32_t)r3 << 24);
                         }
-                        *reinterpret_cast<uint4 *>(stg + c0)      = make_uint4(w[0], w[1], w[2], w[3]);
-                        *reinterpret_cast<uint4 *>(stg + c0 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+                        *reinterpret_cast<uint4 *>(row_s + (c0 ^ sw))        = make_uint4(w[0], w[1], w[2], w[3]);
+                        *reinterpret_cast<uint4 *>(row_s + ((c0 + 16) ^ sw)) = make_uint4(w[4], w[5], w[6], w[7]);
                     }
                     fence_proxy_async(); // generic-proxy writes of this thread -> visible to the async (copy engine) proxy
-                    if (col_ok)
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + h0), "r"(stg_s), "r"(SCAT_ROWS) : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&PM.m[owner]),
+                                     "r"(row0 + h0), "r"(col_w), "r"(tc.unit), "r"(smem_u32(buf_s))
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    scat_buf = (scat_buf + 1 == G8_SCAT_BUFS) ? 0 : scat_buf + 1;
                 }
             } else if constexpr (EPI == EPI_RAW_I32_SCATTER) {
                 // 32 rows x 4 B = 128 B per column and TMEM chunk: same staging row, one bulk copy per chunk
@@ -841,6 +863,19 @@ static bool make_plane_map(CUtensorMap *map, const void *base, size_t k_pad, siz
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// store view of one owner's receive area: {ldc bytes of a column, owner_cols columns, units}, box = 128 rows x 32 columns (one epilogue
+// warp's staging buffer), SWIZZLE_128B to match the conflict-free staging layout
+static bool make_store_map(CUtensorMap *map, void *base, size_t ldc, size_t cols, size_t units, size_t unit_stride) {
+    PFN_encodeTiled enc = get_encoder();
+    if (!enc) return false;
+    cuuint64_t dims[3]    = {(cuuint64_t)ldc, (cuuint64_t)cols, (cuuint64_t)units};
+    cuuint64_t strides[2] = {(cuuint64_t)ldc, (cuuint64_t)(units > 1 ? unit_stride : ldc * cols)};
+    cuuint32_t box[3]     = {128, 32, 1};
+    cuuint32_t estr[3]    = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int num_sms() {
     static std::atomic<int> n[64]; // racing first calls store the same value
     int dev = 0;
@@ -876,6 +911,7 @@ template <int EPI, int CG> static int launch_tc_cg(const GemmArgs &g, cudaStream
     if (!make_plane_map(&mapC, g.A, g.k_pad, g.m, planes, g.strideA, KS::TILE_COL / CG)) return (int)cudaErrorNotSupported;
 
     KParams P{};
+    PeerMaps PM{};
     P.tiles_l       = (int)((g.n + TILE_LANE * CG - 1) / (TILE_LANE * CG));
     P.tiles_c       = (int)((g.m + KS::TILE_COL - 1) / KS::TILE_COL);
     P.num_units     = g.num_units;
@@ -898,6 +934,13 @@ template <int EPI, int CG> static int launch_tc_cg(const GemmArgs &g, cudaStream
         if (g.owner_cols % (TILE_LANE * CG) || (EPI != EPI_MOD_I8_SCATTER && EPI != EPI_RAW_I32_SCATTER)) return (int)cudaErrorInvalidValue;
         P.owner_cols = (int)g.owner_cols;
         for (int i = 0; i < G8_MAX_PEERS; ++i) P.peer_out[i] = g.peer_out[i];
+        if (EPI == EPI_MOD_I8_SCATTER) {
+            if (g.world < 1 || g.world > G8_MAX_PEERS || g.ldc % 16 || g.out_stride % 16) return (int)cudaErrorInvalidValue;
+            for (int o = 0; o < g.world; ++o) {
+                if (!g.peer_out[o] || (reinterpret_cast<uintptr_t>(g.peer_out[o]) & 15)) return (int)cudaErrorInvalidValue;
+                if (!make_store_map(&PM.m[o], g.peer_out[o], g.ldc, g.owner_cols, (size_t)g.num_units, g.out_stride)) return (int)cudaErrorNotSupported;
+            }
+        }
         P.tl_rot = (int)(((size_t)(g.rank + 1) % (size_t)g.world) * (g.owner_cols / (TILE_LANE * CG))) % P.tiles_l;
     }
 
@@ -918,7 +961,7 @@ template <int EPI, int CG> static int launch_tc_cg(const GemmArgs &g, cudaStream
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    return (int)cudaLaunchKernelEx(&cfg, gemm_i8_tc_kernel<EPI, CG>, mapL, mapC, P);
+    return (int)cudaLaunchKernelEx(&cfg, gemm_i8_tc_kernel<EPI, CG>, mapL, mapC, P, PM);
 }
 
 template <int EPI> static int launch_tc(const GemmArgs &g, cudaStream_t st) {
