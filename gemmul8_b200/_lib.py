@@ -64,6 +64,7 @@ SYMBOLS = {
     "g8_mg_comm_status": (c_int, [c_void_p]),
     "g8_mg_comm_destroy": (c_int, [c_void_p]),
     "g8_mg_plan_create": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_int, c_int, c_int, c_size_t, c_size_t, c_size_t, c_uint, c_int]),
+    "g8_mg_plan_create_backend": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_int, c_int, c_int, c_int, c_size_t, c_size_t, c_size_t, c_uint, c_int]),
     "g8_gemm_mg": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p]),
     "g8_mg_plan_destroy": (c_int, [c_void_p]),
     "g8_randmat": (c_int, [c_int, c_void_p, c_size_t, c_size_t, c_double, ctypes.c_ulonglong, c_void_p]),

@@ -481,6 +481,38 @@ void launch_i8_cplx_combine_parts(const int8_t *parts, int nparts, size_t part_s
     i8_cplx_combine_parts_kernel<<<grid, 256, 0, st>>>(parts, nparts, part_stride, elems_per_unit, first_modulus, C_mid, out_stride);
 }
 
+// K-sharded FP8 (real and complex): sum of the per-shard C_mid arrays (each already a canonical residue of that shard's partial product),
+// reduced again: mod_i32 maps every member of a residue class to the same representative in (-p/2, p/2], so the owner's C_mid is
+// bit-identical to what the single-GPU call computes from the un-sharded products.  8 int16 per thread, 128-bit accesses.
+__global__ void __launch_bounds__(256) i16_sum_parts_kernel(const int16_t *__restrict__ parts, int nparts, size_t part_stride, size_t elems_per_unit,
+                                                            int first_modulus, int16_t *__restrict__ C_mid, size_t out_stride) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i * 8 >= elems_per_unit) return;
+    const int u = blockIdx.y, midx = first_modulus + u;
+    const int32_t p = g8d_moduli[FP8][midx], pinv = g8d_pinv32[FP8][midx];
+    const int16_t *src = parts + (size_t)u * elems_per_unit + i * 8;
+    int32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int s = 0; s < nparts; ++s) {
+        const uint4 v       = __ldcs(reinterpret_cast<const uint4 *>(src + (size_t)s * part_stride));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += (int32_t)(int16_t)(w[j >> 1] >> ((j & 1) * 16));
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        const int32_t a = mod_i32(acc[j], p, pinv), b = mod_i32(acc[j + 1], p, pinv);
+        o[j >> 1]       = (uint32_t)(a & 0xFFFF) | ((uint32_t)b << 16);
+    }
+    *reinterpret_cast<uint4 *>(C_mid + (size_t)u * out_stride + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+void launch_i16_sum_parts(const int16_t *parts, int nparts, size_t part_stride, size_t elems_per_unit, int num_units, int first_modulus, int16_t *C_mid,
+                          size_t out_stride, cudaStream_t st) {
+    if (elems_per_unit == 0 || num_units == 0) return;
+    const dim3 grid((unsigned)((elems_per_unit / 8 + 255) / 256), (unsigned)num_units);
+    i16_sum_parts_kernel<<<grid, 256, 0, st>>>(parts, nparts, part_stride, elems_per_unit, first_modulus, C_mid, out_stride);
+}
+
 void launch_i8_cplx_combine(const int8_t *prod, size_t elems_per_unit, int num_units, int first_modulus, int8_t *C_mid, size_t out_stride,
                             cudaStream_t st) {
     const size_t groups = elems_per_unit / 16;

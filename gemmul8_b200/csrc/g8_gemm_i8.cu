@@ -300,7 +300,7 @@ struct KParams {
     int owner_cols;
     int prods, set_stride; // EPI_F8_PROD
     int l2hint; // bit 0: evict_last for the band (lane-side) operand loads; bit 1: evict_first for the column-side panels; bit 2: streaming C_mid stores
-    int kchain; // EPI_BOUND_MAX only: the accumulator sums `kchain` plane pairs (plane c of both operands = K-slab c of a K-sharded bound product)
+    int kchain; // bound epilogues: the accumulator sums `kchain` plane pairs (plane c of both operands = K-slab c of a K-sharded bound product)
     int group;  // lane tiles per rasterisation band (tile_coord)
     int tl_rot; // rotation of the lane-tile sweep so that the ranks do not all target the same owner at the same time
 };
@@ -324,6 +324,13 @@ template <int EPI> __device__ __forceinline__ void chain_groups(int acc, int c, 
 struct PeerMaps {
     CUtensorMap m[G8_MAX_PEERS];
 };
+
+// products chained into one accumulator: the bound epilogues sum `kchain` gathered K-slabs (K-sharded multi-GPU; 1 in the single-GPU call)
+template <int EPI> __device__ __forceinline__ int chain_len(int kchain) {
+    if constexpr (EPI == EPI_BOUND_MAX || EPI == EPI_F8_BOUND) return kchain;
+    else if constexpr (EPI == EPI_BOUND_MAX_CPLX || EPI == EPI_F8_BOUND_CPLX) return 2 * kchain;
+    else return EpiCfg<EPI>::NCHAIN;
+}
 
 template <int EPI, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -386,7 +393,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
             const bool hintL = P.l2hint & 1, hintC = P.l2hint & 2;
             for (int t = cid; t < total_tiles; t += ncl) {
                 const TileCoord tc = tile_coord(t, P.tiles_l, P.tiles_c, P.tl_rot, P.group);
-                const int nchain = (EPI == EPI_BOUND_MAX) ? P.kchain : (EPI == EPI_BOUND_MAX_CPLX) ? 2 * P.kchain : EC::NCHAIN;
+                const int nchain = chain_len<EPI>(P.kchain);
                 for (int acc = 0; acc < EC::NACC; ++acc)
                     for (int c = 0; c < nchain; ++c) {
                         int planeA, planeB;
@@ -408,9 +415,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                             // Re / Im / Re+Im of BOTH operands selected by q
                             const int q = tc.unit % P.prods, mu = tc.unit / P.prods;
                             planeA = P.groupA[q] + mu, planeB = P.groupB[q] + mu;
-                        } else if constexpr (EPI == EPI_BOUND_MAX) {
+                        } else if constexpr (EPI == EPI_BOUND_MAX || EPI == EPI_F8_BOUND) {
                             planeA = P.groupA[0] + tc.unit + c, planeB = P.groupB[0] + tc.unit + c; // chained K-slabs (c = 0 only in the single-GPU call)
-                        } else if constexpr (EPI == EPI_BOUND_MAX_CPLX) {
+                        } else if constexpr (EPI == EPI_BOUND_MAX_CPLX || EPI == EPI_F8_BOUND_CPLX) {
                             // K-slab c / 2 of the gathered planes [slab][|Re|, |Im|]; inside a slab the two products of chain_groups
                             int ga, gb;
                             chain_groups<EPI>(acc, c & 1, ga, gb);
@@ -457,7 +464,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * TILE_COL;
                     uint32_t accumulate   = 0;
-                    const int nchain      = (EPI == EPI_BOUND_MAX) ? P.kchain : (EPI == EPI_BOUND_MAX_CPLX) ? 2 * P.kchain : EC::NCHAIN;
+                    const int nchain      = chain_len<EPI>(P.kchain);
                     for (int c = 0; c < nchain; ++c)
                         for (int kb = 0; kb < P.kblocks; ++kb) {
                             mbar_wait(&full_bar[stage], phase);
@@ -902,8 +909,8 @@ template <int EPI, int CG> static int launch_tc_cg(const GemmArgs &g, cudaStream
     int planes = g.num_units;
     const int mods = ((EPI == EPI_MOD_I8 || EPI == EPI_MOD_I8_SCATTER) && g.prods > 1) ? (g.num_units + g.prods - 1) / g.prods : g.num_units;
     for (int i = 0; i < 3; ++i) planes = max(planes, max(g.groupA[i], g.groupB[i]) + mods);
-    if (EPI == EPI_BOUND_MAX) planes = max(planes, max(g.groupA[0], g.groupB[0]) + g.num_units - 1 + max(1, g.kchain));
-    if (EPI == EPI_BOUND_MAX_CPLX) planes = max(planes, 2 * max(1, g.kchain));
+    if (EPI == EPI_BOUND_MAX || EPI == EPI_F8_BOUND) planes = max(planes, max(g.groupA[0], g.groupB[0]) + g.num_units - 1 + max(1, g.kchain));
+    if (EPI == EPI_BOUND_MAX_CPLX || EPI == EPI_F8_BOUND_CPLX) planes = max(planes, 2 * max(1, g.kchain));
     if (EPI == EPI_F8_MOD) planes = max(g.groupA[0], g.groupB[0]) + f8_plane_base(g.first_modulus + g.num_units);
     if (EPI == EPI_F8_PROD) planes = (g.prods / 3 - 1) * g.set_stride + f8_plane_base(g.first_modulus + (g.num_units + g.prods - 1) / g.prods);
     CUtensorMap mapL, mapC;

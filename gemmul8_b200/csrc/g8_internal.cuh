@@ -23,7 +23,8 @@ void launch_split(const SplitArgs &a, int dtype, int mode, cudaStream_t st);
 void launch_finalize_accu_shift(int16_t *sft, const int32_t *cmax, size_t count, int num_moduli, cudaStream_t st, int backend = INT8);
 // K-sharded multi-GPU support
 void launch_stats(const SplitArgs &a, int dtype, double *amax, double *sumsq, cudaStream_t st);
-void launch_shift_from_stats(const double *amax, const double *sumsq, size_t count, int num_moduli, int kind, int16_t *sft, cudaStream_t st);
+void launch_shift_from_stats(const double *amax, const double *sumsq, size_t count, int num_moduli, int kind, int16_t *sft, cudaStream_t st,
+                             int backend = INT8);
 
 // ---- stage 2: low-precision GEMMs -------------------------------------------------------------
 // One "unit" is one output tile set: for unit u the kernel accumulates `nchain` products
@@ -117,6 +118,11 @@ void launch_f8_combine(const int16_t *prod, bool cplx, size_t elems_per_unit, in
 // K-sharded complex INT8: `nparts` per-shard arrays [modulus][rr, ii, ss][elems] (part_stride BYTES apart) -> summed, reduced, recombined
 void launch_i8_cplx_combine_parts(const int8_t *parts, int nparts, size_t part_stride, size_t elems_per_unit, int num_units, int first_modulus, int8_t *C_mid,
                                   size_t out_stride, cudaStream_t st);
+
+// K-sharded FP8: `nparts` per-shard int16 residue arrays [modulus][elems] (part_stride ELEMENTS apart; complex: {re, im} interleaved,
+// elems counts int16 values) -> summed over the shards and reduced to the canonical symmetric residue mod p (what f8_combine writes)
+void launch_i16_sum_parts(const int16_t *parts, int nparts, size_t part_stride, size_t elems_per_unit, int num_units, int first_modulus, int16_t *C_mid,
+                          size_t out_stride, cudaStream_t st);
 
 // ---- orchestration pieces shared by g8_gemm (g8_api.cu), the host-buffer pipeline (g8_host.cu) and the multi-GPU driver (g8_mg.cu) ----
 struct ContractArgs {

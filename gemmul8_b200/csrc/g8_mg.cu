@@ -11,6 +11,9 @@
 //   * rank barrier  : the same flag exchange without data (`mg_barrier_kernel`).
 // The host only needs a way to pass one 64-byte IPC handle per rank around at start-up (any transport: a pipe, a file, MPI ...).
 //
+// FP8 backend (run_f8): the piece products are contracted and recombined locally into int16 residues (the single-GPU contract()), the
+// owners' column slabs travel as plain peer copies, and the owner sums the shards mod p before the FP8 CRT; K_total <= 2^16.
+//
 // Exactness: |sum| <= K_total * 2^14 < 2^31 requires K_total = world * k_local <= 2^17.  Accurate mode is bit-identical to the
 // single-GPU g8_gemm on the concatenated operands (max and integer sums are order-free); fast mode may differ in a shift on a floor()
 // boundary (its sum of squares is reduced per shard, then across shards), and is then identical on all ranks.
@@ -112,7 +115,11 @@ template <typename T, int OP> static int comm_allreduce(MgComm &c, const T *src,
 
 struct MgPlan {
     MgComm *comm = nullptr;
-    int dtype = F64, opA = OP_N, opB = OP_N, fast = 0;
+    int dtype = F64, opA = OP_N, opB = OP_N, fast = 0, backend = INT8;
+    size_t nmat = 0;               // planes per plane set (INT8: N; FP8: 2 or 3 e4m3 pieces per modulus)
+    int8_t *scratch = nullptr;     // FP8: per-product residues of a batch of moduli (contract())
+    size_t scratch_bytes = 0;
+    int8_t *C_loc = nullptr;       // FP8: this rank's partial C_mid for ALL n columns, int16 [modulus][n][m_pad] (complex: {re, im})
     size_t m = 0, n = 0, k = 0, m_pad = 0, k_pad = 0, n_pad = 0, nc = 0, sizeA = 0, sizeB = 0;
     unsigned N = 0;
     bool cplx = false;
@@ -138,7 +145,8 @@ struct MgPlan {
 
 static void plan_free(MgPlan *p) {
     if (!p) return;
-    for (void *q : {(void *)p->A_lo, (void *)p->B_lo, (void *)p->C_mid, (void *)p->sftA, (void *)p->sftB, (void *)p->stat, (void *)p->maxes})
+    for (void *q : {(void *)p->A_lo, (void *)p->B_lo, (void *)p->C_mid, (void *)p->sftA, (void *)p->sftB, (void *)p->stat, (void *)p->maxes, (void *)p->scratch,
+                    (void *)p->C_loc})
         if (q) cudaFree(q);
     if (p->comm)
         for (int o = 0; o < p->comm->world; ++o)
@@ -170,15 +178,18 @@ static int comm_exchange_host(MgComm &c, const void *mine, size_t bytes, void *a
     return e;
 }
 
-static int plan_create(MgPlan **out, MgComm *c, int dtype, int opA, int opB, size_t m, size_t n, size_t k_local, unsigned N, int fast) {
+static int plan_create(MgPlan **out, MgComm *c, int dtype, int backend, int opA, int opB, size_t m, size_t n, size_t k_local, unsigned N, int fast) {
+    if (backend != INT8 && backend != FP8) return G8_STATUS_INVALID_VALUE;
     if (!out || !c || !c->connected || dtype < F32 || dtype > C64 || opA < 0 || opA > 2 || opB < 0 || opB > 2) return G8_STATUS_INVALID_VALUE;
     if (N < 2 || N > G8_MAX_MODULI || m == 0 || n == 0 || k_local == 0) return G8_STATUS_INVALID_VALUE;
     const size_t W = (size_t)c->world;
     if (n % W || (n / W) % 256) return G8_STATUS_INVALID_VALUE;              // the scatter hands whole 256-column tiles to one owner
     if (W * k_local > (size_t(1) << 17)) return G8_STATUS_INVALID_VALUE;       // INT32 accumulation bound over the TOTAL K
+    if (backend == FP8 && W * k_local > (size_t(1) << 16)) return G8_STATUS_INVALID_VALUE; // binary32 accumulation of the piece products (g8_gemm)
     if (!device_supported_cached()) return G8_STATUS_NO_DEVICE_CODE;
     MgPlan *p = new (std::nothrow) MgPlan();
     if (!p) return (int)cudaErrorMemoryAllocation;
+    p->backend = backend, p->nmat = num_planes(backend, N);
     p->comm = c, p->dtype = dtype, p->opA = opA, p->opB = opB, p->fast = fast, p->m = m, p->n = n, p->k = k_local, p->N = N;
     p->m_pad = pad256(m), p->k_pad = pad256(k_local), p->n_pad = pad256(n), p->nc = n / W;
     p->sizeA = p->k_pad * p->m_pad, p->sizeB = p->k_pad * n;
@@ -193,9 +204,16 @@ static int plan_create(MgPlan **out, MgComm *c, int dtype, int opA, int opB, siz
     };
 #define G8_ALLOC(ptr, bytes) \
     if (cudaMalloc(reinterpret_cast<void **>(&(ptr)), (bytes)) != cudaSuccess) return fail((int)cudaErrorMemoryAllocation)
-    G8_ALLOC(p->A_lo, p->sizeA * N * p->sets);
-    G8_ALLOC(p->B_lo, p->sizeB * N * p->sets);
-    if (p->cplx) G8_ALLOC(p->C_mid, 2 * (size_t)N * p->nc * p->m_pad);
+    const size_t mid = (backend == FP8 ? 2 : 1) * (p->cplx ? 2 : 1); // bytes per C_mid element
+    G8_ALLOC(p->A_lo, p->sizeA * p->nmat * p->sets);
+    G8_ALLOC(p->B_lo, p->sizeB * p->nmat * p->sets);
+    if (p->cplx || backend == FP8) G8_ALLOC(p->C_mid, mid * (size_t)N * p->nc * p->m_pad);
+    if (backend == FP8) {
+        G8_ALLOC(p->C_loc, mid * (size_t)N * n * p->m_pad);
+        const size_t per_mod = (p->cplx ? 9 : 3) * sizeof(int16_t) * p->m_pad * n; // contract(): per-product residues of one modulus
+        p->scratch_bytes     = per_mod * std::min<size_t>(N, 4);
+        G8_ALLOC(p->scratch, p->scratch_bytes);
+    }
     G8_ALLOC(p->sftA, sizeof(int16_t) * p->m_pad);
     G8_ALLOC(p->sftB, sizeof(int16_t) * p->n_pad);
     G8_ALLOC(p->stat, sizeof(double) * 4 * (m + n));
@@ -205,7 +223,8 @@ static int plan_create(MgPlan **out, MgComm *c, int dtype, int opA, int opB, siz
     if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess)
         return fail((int)cudaErrorUnknown);
-    const size_t per = p->sets * (size_t)N * n * p->m_pad; // W shards x (N moduli [x 3 products]) x nc columns x m_pad rows (int8)
+    // INT8: W shards x (N moduli [x 3 products]) x nc columns x m_pad rows (int8); FP8: W shards x N moduli x nc x m_pad C_mid elements
+    const size_t per = backend == FP8 ? mid * (size_t)N * n * p->m_pad : p->sets * (size_t)N * n * p->m_pad;
     p->abar_off   = per;
     p->bbar_off   = per + W * p->bsets * p->sizeA;
     p->recv_bytes = per + (fast ? 0 : W * p->bsets * (p->sizeA + p->nc * p->k_pad));
@@ -226,7 +245,10 @@ static int plan_create(MgPlan **out, MgComm *c, int dtype, int opA, int opB, siz
     return 0;
 }
 
+static int run_f8(MgPlan &p, const void *alpha, const void *A, size_t lda, const void *B, size_t ldb, const void *beta, void *C, size_t ldc, cudaStream_t st);
+
 static int run(MgPlan &p, const void *alpha, const void *A, size_t lda, const void *B, size_t ldb, const void *beta, void *C, size_t ldc, cudaStream_t st) {
+    if (p.backend == FP8) return run_f8(p, alpha, A, lda, B, ldb, beta, C, ldc, st);
     MgComm &c = *p.comm;
     const size_t m = p.m, n = p.n, k = p.k, W = (size_t)c.world, nc = p.nc, mp = p.m_pad;
     const unsigned N = p.N;
@@ -328,6 +350,107 @@ static int run(MgPlan &p, const void *alpha, const void *A, size_t lda, const vo
     return (int)cudaPeekAtLastError();
 }
 
+
+// ---- FP8 backend ----
+// Same shift protocol as the INT8 path (global statistics; accurate mode: gathered e4m3 bound planes, bound GEMM chained over the K-slabs in
+// rank order -- the binary32 accumulation then performs the same sequence of MMAs as the single-GPU call whenever k_local is a multiple of
+// 32, the extra zero padding of each slab adding exact zeros).  Contraction: the single-GPU contract() over all n columns into a local
+// int16 C_mid; exchange: one strided peer copy per owner; owner: shard sum mod p (i16_sum_parts) + the FP8 CRT.
+static int run_f8(MgPlan &p, const void *alpha, const void *A, size_t lda, const void *B, size_t ldb, const void *beta, void *C, size_t ldc, cudaStream_t st) {
+    MgComm &c = *p.comm;
+    const size_t m = p.m, n = p.n, k = p.k, W = (size_t)c.world, nc = p.nc, mp = p.m_pad;
+    const unsigned N = p.N;
+    if (!alpha || !beta || !A || !B || !C) return G8_STATUS_INVALID_VALUE;
+    double *amax = p.stat, *ss = p.stat + (m + n), *amax_r = p.stat + 2 * (m + n), *ss_r = p.stat + 3 * (m + n);
+    auto fork = [&]() -> int {
+        G8_TRY(cudaEventRecord(p.ev_fork, st));
+        return (int)cudaStreamWaitEvent(p.side, p.ev_fork, 0);
+    };
+    auto join = [&]() -> int {
+        G8_TRY(cudaEventRecord(p.ev_join, p.side));
+        return (int)cudaStreamWaitEvent(st, p.ev_join, 0);
+    };
+    const SplitArgs sa = make_split_args(1, p.opA, m, k, A, lda, N, p.sftA, p.A_lo, p.sizeA, p.nmat, FP8);
+    const SplitArgs sb = make_split_args(0, p.opB, n, k, B, ldb, N, p.sftB, p.B_lo, p.sizeB, p.nmat, FP8);
+
+    G8_TRY(fork());
+    launch_stats(sa, p.dtype, amax, ss, st);
+    launch_stats(sb, p.dtype, amax + m, ss + m, p.side);
+    G8_TRY(join());
+    G8_TRY((comm_allreduce<double, 0>(c, amax, amax_r, m + n, st)));
+    if (p.fast) {
+        G8_TRY((comm_allreduce<double, 1>(c, ss, ss_r, m + n, st)));
+        G8_TRY(fork());
+        launch_shift_from_stats(amax_r, ss_r, m, (int)N, 0, p.sftA, st, FP8);
+        launch_shift_from_stats(amax_r + m, ss_r + m, n, (int)N, 0, p.sftB, p.side, FP8);
+    } else {
+        G8_TRY(fork());
+        SplitArgs ea = sa, eb = sb; // bound planes alias plane 0 (,1) of the residue planes
+        for (int g = 0; g < 3; ++g) ea.planes[g] = p.A_lo + g * p.sizeA, eb.planes[g] = p.B_lo + g * p.sizeB;
+        launch_shift_from_stats(amax_r, nullptr, m, (int)N, 1, p.sftA, st, FP8);
+        launch_split(ea, p.dtype, 3, st);
+        launch_shift_from_stats(amax_r + m, nullptr, n, (int)N, 1, p.sftB, p.side, FP8);
+        launch_split(eb, p.dtype, 3, p.side);
+        const size_t bslab = nc * p.k_pad, bs = p.bsets;
+        for (size_t j = 0; j < W; ++j) {
+            const size_t o = ((size_t)c.rank + j) % W;
+            G8_TRY(cudaMemcpyAsync(p.peer_recv[o] + p.abar_off + (size_t)c.rank * bs * p.sizeA, p.A_lo, bs * p.sizeA, cudaMemcpyDefault, st));
+        }
+        G8_TRY(join());
+        for (size_t j = 0; j < W; ++j) {
+            const size_t o = ((size_t)c.rank + j) % W;
+            for (size_t g = 0; g < bs; ++g)
+                G8_TRY(cudaMemcpyAsync(p.peer_recv[o] + p.bbar_off + ((size_t)c.rank * bs + g) * bslab, p.B_lo + g * p.sizeB + o * bslab, bslab, cudaMemcpyDefault, st));
+        }
+        G8_TRY(comm_barrier(c, st));
+        int32_t *mx = p.maxes, *mx_r = p.maxes + (p.m_pad + p.n_pad);
+        G8_TRY(cudaMemsetAsync(mx, 0, sizeof(int32_t) * (p.m_pad + p.n_pad), st));
+        GemmArgs g{};
+        g.A = reinterpret_cast<const int8_t *>(p.recv + p.abar_off), g.B = reinterpret_cast<const int8_t *>(p.recv + p.bbar_off);
+        g.strideA = p.sizeA, g.strideB = bslab, g.m = m, g.n = nc, g.m_pad = mp, g.k_pad = p.k_pad;
+        g.num_units = 1, g.first_modulus = 0, g.epi = p.cplx ? EPI_F8_BOUND_CPLX : EPI_F8_BOUND, g.kchain = (int)W;
+        g.k_true = (int)(W * k); // the inflation factor (k + 1) * 2^-24 of the un-sharded product
+        g.groupA[0] = 0, g.groupA[1] = 1, g.groupA[2] = 2, g.groupB[0] = 0, g.groupB[1] = 1, g.groupB[2] = 2;
+        if (!p.cplx) g.groupA[1] = g.groupA[2] = g.groupB[1] = g.groupB[2] = 0;
+        g.ldc = mp, g.rowmax = mx, g.colmax = mx + p.m_pad + (size_t)c.rank * nc;
+        G8_TRY(launch_gemm_tc(g, st));
+        // the maxima are non-negative floats stored by their bit pattern: the integer MAX all-reduce orders them correctly
+        G8_TRY((comm_allreduce<int32_t, 0>(c, mx, mx_r, p.m_pad + p.n_pad, st)));
+        G8_TRY(fork());
+        launch_finalize_accu_shift(p.sftA, mx_r, m, (int)N, st, FP8);
+        launch_finalize_accu_shift(p.sftB, mx_r + p.m_pad, n, (int)N, p.side, FP8);
+    }
+    launch_split(sa, p.dtype, 0, st);
+    launch_split(sb, p.dtype, 0, p.side);
+    G8_TRY(join());
+
+    // ---- contraction of my K-slab for all n columns, then every owner's column slab of every modulus travels as one strided peer copy ----
+    const size_t esz = sizeof(int16_t) * (p.cplx ? 2 : 1), slab = nc * mp * esz;
+    ContractArgs ca{};
+    ca.cplx = p.cplx, ca.backend = FP8, ca.N = N, ca.m = m, ca.ncols = n, ca.m_pad = mp, ca.k_pad = p.k_pad;
+    ca.A_lo = p.A_lo, ca.B_lo = p.B_lo, ca.sizeA = p.sizeA, ca.sizeB = p.sizeB, ca.set_planes = p.nmat;
+    ca.C_mid = p.C_loc, ca.mid_plane_stride = mp * n, ca.scratch = p.scratch, ca.scratch_avail = p.scratch_bytes;
+    G8_TRY(contract(ca, st));
+    for (size_t j = 0; j < W; ++j) {
+        const size_t o = ((size_t)c.rank + j) % W;
+        char *dst = p.peer_recv[o] + (size_t)c.rank * N * slab;
+        if (W * slab < (size_t(1) << 31)) { // pitch limit of the 2-D copy
+            G8_TRY(cudaMemcpy2DAsync(dst, slab, p.C_loc + o * slab, W * slab, slab, N, cudaMemcpyDefault, st));
+        } else {
+            for (size_t u = 0; u < N; ++u) G8_TRY(cudaMemcpyAsync(dst + u * slab, p.C_loc + (u * W + o) * slab, slab, cudaMemcpyDefault, st));
+        }
+    }
+    G8_TRY(comm_barrier(c, st));
+    const size_t unit_elems = nc * mp * (p.cplx ? 2 : 1); // int16 values per modulus of my slab
+    launch_i16_sum_parts(reinterpret_cast<const int16_t *>(p.recv), (int)W, (size_t)N * unit_elems, unit_elems, (int)N, 0, reinterpret_cast<int16_t *>(p.C_mid),
+                         unit_elems, st);
+    CrtArgs cr{};
+    cr.C_mid = p.C_mid, cr.ldmid = mp, cr.plane_stride = nc * mp, cr.m = m, cr.n = nc, cr.num_moduli = (int)N;
+    cr.C = C, cr.ldc = ldc, cr.sftA = p.sftA, cr.sftB = p.sftB + (size_t)c.rank * nc, cr.alpha = alpha, cr.beta = beta, cr.backend = FP8;
+    G8_TRY(launch_crt(cr, p.dtype, st));
+    return (int)cudaPeekAtLastError();
+}
+
 } // namespace g8
 
 using namespace g8;
@@ -393,8 +516,13 @@ __attribute__((visibility("default"))) int g8_mg_comm_destroy(g8_mg_comm *comm) 
 
 __attribute__((visibility("default"))) int g8_mg_plan_create(g8_mg_plan **plan, g8_mg_comm *comm, int dtype, int op_A, int op_B, size_t m, size_t n, size_t k_local,
                                                               unsigned num_moduli, int fastmode) {
+    return g8_mg_plan_create_backend(plan, comm, dtype, G8_BACKEND_INT8, op_A, op_B, m, n, k_local, num_moduli, fastmode);
+}
+
+__attribute__((visibility("default"))) int g8_mg_plan_create_backend(g8_mg_plan **plan, g8_mg_comm *comm, int dtype, int backend, int op_A, int op_B, size_t m, size_t n,
+                                                                      size_t k_local, unsigned num_moduli, int fastmode) {
     MgPlan *p = nullptr;
-    const int e = plan_create(&p, reinterpret_cast<MgComm *>(comm), dtype, op_A, op_B, m, n, k_local, num_moduli, fastmode != 0);
+    const int e = plan_create(&p, reinterpret_cast<MgComm *>(comm), dtype, backend, op_A, op_B, m, n, k_local, num_moduli, fastmode != 0);
     if (e == 0) *plan = reinterpret_cast<g8_mg_plan *>(p);
     return e;
 }

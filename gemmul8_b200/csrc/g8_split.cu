@@ -806,15 +806,15 @@ template <typename T> __global__ void __launch_bounds__(1024) stats_only_rowstri
     if (row < (int)a.rows && x == 0) amax_out[row] = dmax, sumsq_out[row] = sum;
 }
 // kind 0: fast-mode shift from (amax, sumsq); kind 1: accurate-mode s0 from amax
-__global__ void shift_from_stats_kernel(const double *amax, const double *sumsq, int count, int num_moduli, int kind, int16_t *sft) {
+__global__ void shift_from_stats_kernel(const double *amax, const double *sumsq, int count, int num_moduli, int kind, int16_t *sft, int backend) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     if (kind == 0) {
         // the cross-rank sum was rounded to nearest: nudge it up so the Cauchy-Schwarz bound stays rigorous
         const double s = sumsq[i] * (1.0 + 0x1p-48);
-        sft[i] = (int16_t)(-fast_shift(amax[i], s, g8d_log2P[INT8][num_moduli]));
+        sft[i] = (int16_t)(-fast_shift(amax[i], s, g8d_log2P[backend][num_moduli]));
     } else {
-        sft[i] = (int16_t)accu_s0(amax[i]);
+        sft[i] = (int16_t)(accu_s0(amax[i]) + (backend == FP8 ? 2 : 0)); // maxUFP: 5 (INT8) / 7 (FP8), template_type.hpp:147
     }
 }
 
@@ -831,8 +831,8 @@ void launch_stats(const SplitArgs &a, int dtype, double *amax, double *sumsq, cu
     }
 #undef G8_STATS
 }
-void launch_shift_from_stats(const double *amax, const double *sumsq, size_t count, int num_moduli, int kind, int16_t *sft, cudaStream_t st) {
-    shift_from_stats_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(amax, sumsq, (int)count, num_moduli, kind, sft);
+void launch_shift_from_stats(const double *amax, const double *sumsq, size_t count, int num_moduli, int kind, int16_t *sft, cudaStream_t st, int backend) {
+    shift_from_stats_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(amax, sumsq, (int)count, num_moduli, kind, sft, backend);
 }
 
 void launch_finalize_accu_shift(int16_t *sft, const int32_t *cmax, size_t count, int num_moduli, cudaStream_t st, int backend) {

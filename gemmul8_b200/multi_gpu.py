@@ -439,12 +439,13 @@ class NativeKShardGemm:
     orchestration in C++, every inter-rank exchange through the library's own kernels over NVLink peer memory (fused GEMM -> scatter,
     mailbox all-reduce in fixed rank order, flag barrier) -- no NCCL on the path.  torch.distributed is used ONCE, at construction, to
     pass the 64-byte IPC handles around (any transport would do; tests/native/mg_check.cu uses a shared mapping and no Python at all).
-    Same interface as KShardGemm."""
+    Same interface as KShardGemm.  backend=Backend.FP8: local contraction into int16 residues, peer copies of the owners' slabs, shard
+    sum mod p on the owner (world * k_local <= 2^16)."""
 
-    def __init__(self, m, n, k_local, num_moduli, fastmode=False, dtype=torch.float64, device=None, group=None, op_A="N", op_B="N"):
+    def __init__(self, m, n, k_local, num_moduli, fastmode=False, dtype=torch.float64, device=None, group=None, op_A="N", op_B="N", backend=0):
         from . import _lib
         if dtype not in api._DTYPES:
-            raise NotImplementedError("K-sharded path: S/D/C/Z GEMM (INT8 backend)")
+            raise NotImplementedError("K-sharded path: S/D/C/Z GEMM")
         self.lib, self.group = _lib.load(), group
         self.W, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.m, self.n, self.k, self.N, self.dtype = m, n, k_local, num_moduli, dtype
@@ -461,8 +462,8 @@ class NativeKShardGemm:
             dist.all_gather_object(handles, bytes(handle.raw), group=group)
             api._check(self.lib.g8_mg_comm_connect(self.comm, ctypes.create_string_buffer(b"".join(handles), 64 * self.W)), "g8_mg_comm_connect")
             dist.barrier(group=group)
-            api._check(self.lib.g8_mg_plan_create(ctypes.byref(self.plan), self.comm, api._DTYPES[dtype], self.opA, self.opB, m, n, k_local,
-                                                  num_moduli, int(bool(fastmode))), "g8_mg_plan_create")
+            api._check(self.lib.g8_mg_plan_create_backend(ctypes.byref(self.plan), self.comm, api._DTYPES[dtype], int(backend), self.opA, self.opB, m, n,
+                                                          k_local, num_moduli, int(bool(fastmode))), "g8_mg_plan_create")
         self.lda = m if self.opA == 0 else k_local
         self.ldb = k_local if self.opB == 0 else n
 

@@ -178,7 +178,7 @@ int g8_host_plan_destroy(g8_host_plan *plan);
  *                       problem) and returns its IPC handle in handle64;
  *   g8_mg_comm_connect  takes the world x 64 bytes of all ranks' handles in rank order (its own entry is ignored);
  *   g8_mg_plan_create   COLLECTIVE: allocates the planes and the peer-mapped receive area of one problem shape and exchanges the
- *                       receive-area handles through the communicator.  dtype G8_R32F / G8_R64F, INT8 backend, any op_A / op_B;
+ *                       receive-area handles through the communicator.  All four dtypes, INT8 backend, any op_A / op_B;
  *                       n / world must be a multiple of 256, world * k_local <= 2^17;
  *   g8_gemm_mg          COLLECTIVE, asynchronous on `stream`: every rank passes its slabs (device pointers, column-major, leading
  *                       dimensions lda / ldb) and gets its m x (n / world) slab of C (ld ldc); alpha / beta as in g8_gemm;
@@ -194,6 +194,10 @@ int g8_mg_comm_status(g8_mg_comm *comm);
 int g8_mg_comm_destroy(g8_mg_comm *comm);
 int g8_mg_plan_create(g8_mg_plan **plan, g8_mg_comm *comm, int dtype, int op_A, int op_B, size_t m, size_t n, size_t k_local, unsigned num_moduli,
                       int fastmode);
+/* the same with a backend: G8_BACKEND_FP8 contracts locally into int16 residues, moves the owners' column slabs with peer copies and sums
+ * the shards mod p on the owner; world * k_local <= 2^16; all four dtypes */
+int g8_mg_plan_create_backend(g8_mg_plan **plan, g8_mg_comm *comm, int dtype, int backend, int op_A, int op_B, size_t m, size_t n, size_t k_local,
+                              unsigned num_moduli, int fastmode);
 int g8_gemm_mg(g8_mg_plan *plan, const void *alpha, const void *A_local, size_t lda, const void *B_local, size_t ldb, const void *beta,
                void *C_slab, size_t ldc, void *stream);
 int g8_mg_plan_destroy(g8_mg_plan *plan);

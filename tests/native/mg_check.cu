@@ -36,7 +36,7 @@ static void host_barrier(Shared *sh, int idx, int world) {
         }                                                                          \
     } while (0)
 
-template <typename T> static int run_case(g8_mg_comm *comm, int rank, int world, int dtype, unsigned N, int fast, int opA, int opB) {
+template <typename T> static int run_case(g8_mg_comm *comm, int rank, int world, int dtype, unsigned N, int fast, int opA, int opB, int backend = G8_BACKEND_INT8) {
     const size_t m = 300, n = 256 * (size_t)world, kl = 384, K = kl * world, nc = n / world;
     // full operands, identical on every rank (same seeds): A stored as op_A wants it, likewise B
     const size_t rA = opA == G8_OP_N ? m : K, cA = opA == G8_OP_N ? K : m, rB = opB == G8_OP_N ? K : n, cB = opB == G8_OP_N ? n : K;
@@ -61,16 +61,17 @@ template <typename T> static int run_case(g8_mg_comm *comm, int rank, int world,
     else *reinterpret_cast<double *>(&one) = 1.0;
     const bool cplx = dtype >= G8_C32F;
     // single-GPU reference on the full K
-    const size_t wbytes = g8_work_size(cplx, G8_BACKEND_INT8, m, n, K, N, 0, 0, nullptr, nullptr);
+    const size_t wbytes = g8_work_size(cplx, backend, m, n, K, N, 0, 0, nullptr, nullptr);
     void *work;
     CK(cudaMalloc(&work, wbytes));
     g8_gemm_desc d{};
-    d.dtype = dtype, d.backend = G8_BACKEND_INT8, d.op_A = opA, d.op_B = opB, d.m = m, d.n = n, d.k = K;
+    d.dtype = dtype, d.backend = backend, d.op_A = opA, d.op_B = opB, d.m = m, d.n = n, d.k = K;
     d.alpha = &one, d.A = A, d.lda = rA, d.B = B, d.ldb = rB, d.beta = &zero, d.C = Cfull, d.ldc = m, d.num_moduli = N, d.fastmode = fast, d.work = work;
     CK(g8_gemm(&d, nullptr));
     // sharded
     g8_mg_plan *plan = nullptr;
-    CK(g8_mg_plan_create(&plan, comm, dtype, opA, opB, m, n, kl, N, fast));
+    if (backend == G8_BACKEND_INT8) CK(g8_mg_plan_create(&plan, comm, dtype, opA, opB, m, n, kl, N, fast));
+    else CK(g8_mg_plan_create_backend(&plan, comm, dtype, backend, opA, opB, m, n, kl, N, fast));
     for (int rep = 0; rep < 2; ++rep) CK(g8_gemm_mg(plan, &one, Al, rAl, Bl, rBl, &zero, Cslab, m, nullptr)); // twice: the receive areas are re-used
     CK(cudaDeviceSynchronize());
     CK(g8_mg_comm_status(comm));
@@ -87,7 +88,8 @@ template <typename T> static int run_case(g8_mg_comm *comm, int rank, int world,
         num = std::fmax(num, std::fabs(w - g)), den = std::fmax(den, std::fabs(w));
     }
     const bool ok = fast ? (num <= (dbl ? 1e-9 : 1e-3) * den) : same;
-    std::printf("rank %d: %cGEMM N=%u %s op%d%d  %s (max diff / max = %.2e)\n", rank, "SDCZ"[dtype], N, fast ? "fast" : "accu", opA, opB,
+    std::printf("rank %d: %cGEMM %s N=%u %s op%d%d  %s (max diff / max = %.2e)\n", rank, "SDCZ"[dtype], backend == G8_BACKEND_INT8 ? "INT8" : "FP8", N,
+                fast ? "fast" : "accu", opA, opB,
                 same ? "bit-identical" : (ok ? "within tolerance" : "MISMATCH"), den > 0 ? num / den : 0.0);
     CK(g8_mg_plan_destroy(plan));
     cudaFree(A), cudaFree(B), cudaFree(Cfull), cudaFree(Cslab), cudaFree(Al), cudaFree(Bl), cudaFree(work);
@@ -108,6 +110,9 @@ static int rank_main(Shared *sh, int rank, int world) {
         bad += run_case<float>(comm, rank, world, G8_R32F, 6, fast, G8_OP_N, G8_OP_T);
         bad += run_case<cuDoubleComplex>(comm, rank, world, G8_C64F, 10, fast, G8_OP_N, G8_OP_N);
         bad += run_case<cuFloatComplex>(comm, rank, world, G8_C32F, 6, fast, G8_OP_C, G8_OP_T);
+        // FP8 backend: local contraction into int16 residues, slab copies, shard sum mod p on the owner
+        bad += run_case<double>(comm, rank, world, G8_R64F, 12, fast, G8_OP_T, G8_OP_N, G8_BACKEND_FP8);
+        bad += run_case<cuFloatComplex>(comm, rank, world, G8_C32F, 7, fast, G8_OP_N, G8_OP_C, G8_BACKEND_FP8);
     }
     CK(g8_mg_comm_barrier(comm, nullptr));
     CK(cudaDeviceSynchronize());

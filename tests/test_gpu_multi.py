@@ -48,7 +48,7 @@ def _worker(rank, world, port, q):
             Br = B.view(n, K)[:, rank * kl:(rank + 1) * kl].contiguous().view(-1)          # rows K_r of B
             for fast in (False, True):
                 Cfull = torch.zeros(m * n, dtype=dtype, device=f"cuda:{rank}")
-                tot, _, _ = g8.work_size(m, n, K, N)
+                tot, _, _ = g8.work_size(m, n, K, N, is_complex=dtype.is_complex)
                 work = torch.empty(tot, dtype=torch.uint8, device=f"cuda:{rank}")
                 g8.gemm("N", "N", m, n, K, 1.0, A, m, B, K, 0.0, Cfull, m, N, fast, work)
                 for variant in ("int32", "residue", "fused", "fused-sumpass", "native"):
@@ -82,6 +82,74 @@ def _worker(rank, world, port, q):
         raise
     finally:
         dist.destroy_process_group()
+
+
+def _f8_worker(rank, world, port, q):
+    """FP8 backend, K-sharded through the native driver: accurate mode bit-identical to the single-GPU FP8 call (k_local is a multiple of
+    32, so the chained bound GEMM performs the same binary32 MMA sequence), fast mode to tolerance"""
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import gemmul8_b200 as g8
+        from gemmul8_b200 import multi_gpu
+
+        ok_all = True
+        for dtype, N in ((torch.float64, 12), (torch.float32, 6), (torch.complex128, 8)):
+            m, n, kl = 300, 256 * world, 384
+            K = kl * world
+            A = g8.randmat(m, K, dtype, phi=0.5, seed=51, device=f"cuda:{rank}")
+            B = g8.randmat(K, n, dtype, phi=0.5, seed=52, device=f"cuda:{rank}")
+            Ar = A.view(K, m)[rank * kl:(rank + 1) * kl].contiguous().view(-1)
+            Br = B.view(n, K)[:, rank * kl:(rank + 1) * kl].contiguous().view(-1)
+            for fast in (False, True):
+                Cfull = torch.zeros(m * n, dtype=dtype, device=f"cuda:{rank}")
+                tot, _, _ = g8.work_size(m, n, K, N, is_complex=dtype.is_complex, backend=g8.Backend.FP8)
+                work = torch.empty(tot, dtype=torch.uint8, device=f"cuda:{rank}")
+                g8.gemm("N", "N", m, n, K, 1.0, A, m, B, K, 0.0, Cfull, m, N, fast, work, backend=g8.Backend.FP8)
+                plan = multi_gpu.NativeKShardGemm(m, n, kl, N, fastmode=fast, dtype=dtype, device=f"cuda:{rank}", backend=int(g8.Backend.FP8))
+                C = torch.zeros(plan.local_out_elems, dtype=dtype, device=f"cuda:{rank}")
+                for _ in range(2):
+                    plan.run(Ar, Br, C)
+                torch.cuda.synchronize()
+                plan.close()
+                nc = n // world
+                want = Cfull.view(n, m)[rank * nc:(rank + 1) * nc].reshape(-1)
+                if not fast:
+                    ok = torch.equal(C, want)
+                else:
+                    ok = bool(((C - want).abs().max() / want.abs().max()) < (1e-9 if dtype in (torch.float64, torch.complex128) else 1e-3))
+                ok_all &= ok
+                if not ok:
+                    print(f"rank {rank} FP8 K-shard mismatch dtype={dtype} fast={fast} maxdiff={(C - want).abs().max().item()}", flush=True)
+        q.put((rank, ok_all))
+    except Exception:
+        q.put((rank, False))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_kshard_fp8_native_matches_single_gpu(cuda):
+    import torch.multiprocessing as mp
+
+    world = _world()
+    if world < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_f8_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+    assert all(ok for _, ok in res), res
 
 
 def _nshard_worker(rank, world, port, q):

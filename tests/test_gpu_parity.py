@@ -414,11 +414,13 @@ def test_fp8_tensor_core_accumulation_is_exact(env):
 
 @pytest.mark.parametrize("dtype,N", [(np.float64, 14), (np.float32, 6), (np.complex128, 10), (np.complex64, 6)])
 @pytest.mark.parametrize("fast", [False, True])
-def test_native_kshard_driver_world1_matches_gemm(env, dtype, N, fast):
+@pytest.mark.parametrize("backend", [0, 1])
+def test_native_kshard_driver_world1_matches_gemm(env, dtype, N, fast, backend):
     """The native multi-GPU driver (g8_mg_comm_* / g8_mg_plan_* / g8_gemm_mg, csrc/g8_mg.cu) with a world of ONE rank: the whole path --
     mailbox all-reduce, flag barrier, bound-plane exchange + chained bound GEMM, GEMM -> scatter, owner-side shard sum (+ complex 3M
     recombination) + CRT -- runs on a single GPU and must reproduce g8_gemm: accurate mode bit for bit, fast mode to the documented
-    tolerance (its statistics kernels differ).  (2 - 8 ranks: tests/test_gpu_multi.py and tests/native/mg_check.cu.)"""
+    tolerance (its statistics kernels differ).  backend 1 = FP8: local contraction into int16 residues, slab copies, shard sum mod p, FP8
+    CRT.  (2 - 8 ranks: tests/test_gpu_multi.py and tests/native/mg_check.cu.)"""
     import ctypes
     torch, H = env.torch, env.H
     from gemmul8_b200 import _lib, api
@@ -431,7 +433,7 @@ def test_native_kshard_driver_world1_matches_gemm(env, dtype, N, fast):
     for opA, opB in (("N", "N"), ("T", "C" if cplx else "T")):
         A = H.rand_matrix(rng, H.stored_shape(opA, m, k), dtype)
         B = H.rand_matrix(rng, H.stored_shape(opB, k, n), dtype)
-        want = H.run_gemm(A, B, opA, opB, N, fast)
+        want = H.run_gemm(A, B, opA, opB, N, fast, backend=backend)
         dA, lda = H.to_dev_colmajor(A)
         dB, ldb = H.to_dev_colmajor(B)
         dC, ldc = H.to_dev_colmajor(np.zeros((m, n), dtype=dtype))
@@ -439,7 +441,7 @@ def test_native_kshard_driver_world1_matches_gemm(env, dtype, N, fast):
         handle = ctypes.create_string_buffer(64)
         api._check(lib.g8_mg_comm_create(ctypes.byref(comm), 1, 0, 8 * (m + n) + 4096, handle), "comm_create")
         api._check(lib.g8_mg_comm_connect(comm, handle), "comm_connect")
-        api._check(lib.g8_mg_plan_create(ctypes.byref(plan), comm, api._DTYPES[tdt], api._op(opA), api._op(opB), m, n, k, N, int(fast)), "plan_create")
+        api._check(lib.g8_mg_plan_create_backend(ctypes.byref(plan), comm, api._DTYPES[tdt], backend, api._op(opA), api._op(opB), m, n, k, N, int(fast)), "plan_create")
         keep = []
         pa, pb = api._scalar_ptr(1.0, tdt, keep), api._scalar_ptr(0.0, tdt, keep)
         for _ in range(2):
