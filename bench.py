@@ -448,7 +448,9 @@ def main():
             g.trace_report = lambda: []
             return g
         if args.mg_variant == "native":
-            return multi_gpu.NativeKShardGemm(m, n, k_loc, N, fastmode=fast, dtype=dt, device=dev)
+            return multi_gpu.NativeKShardGemm(m, n, k_loc, N, fastmode=fast, dtype=dt, device=dev, backend=be)
+        if be:
+            raise SystemExit("--backend fp8 with --gpus N > 1: K-shard through the native driver only (--mg-variant native --mg-shard k)")
         return multi_gpu.KShardGemm(m, n, k_loc, N, fastmode=fast, dtype=dt, device=dev, variant=args.mg_variant)
 
     def barrier():
@@ -483,7 +485,7 @@ def main():
     verify = None
     if distributed:
         from gemmul8_b200 import multi_gpu
-        verify = multi_gpu.verify_against_single_gpu(shard, world, rank, dev, N, fast, variant=args.mg_variant)
+        verify = multi_gpu.verify_against_single_gpu(shard, world, rank, dev, N, fast, variant=args.mg_variant, backend=be if shard == "k" else 0)
 
     A, B = make_inputs(k_local, shard)
     mg = make_mg(k_local, shard) if distributed else None

@@ -603,7 +603,7 @@ class NShardGemm:
         return C
 
 
-def verify_against_single_gpu(shard, world, rank, dev, num_moduli, fastmode, variant="fused", m=512, k_local=512):
+def verify_against_single_gpu(shard, world, rank, dev, num_moduli, fastmode, variant="fused", m=512, k_local=512, backend=0):
     """bench.py --gpus N: before anything is timed, run the sharded path on a reduced problem and compare this rank's column slab with
     the SINGLE-GPU g8.gemm on the assembled operands (every rank regenerates all slabs from the seeds, so no gather is needed).
     Accurate mode must match bit for bit; fast mode within 1e-9 (see KShardGemm).  Returns a dict for the bench line."""
@@ -614,7 +614,9 @@ def verify_against_single_gpu(shard, world, rank, dev, num_moduli, fastmode, var
     seedA = lambda r: 777 + (1000 * r if shard == "k" else 0)
     seedB = lambda r: 999 + (1000 * r if shard in ("k", "n") else 0)
     if shard == "k":
-        g = (NativeKShardGemm(m, n, k_local, num_moduli, fastmode=fastmode, dtype=dt, device=dev) if variant == "native" else
+        if backend and variant != "native":
+            raise NotImplementedError("FP8 K-shard: the native driver only")
+        g = (NativeKShardGemm(m, n, k_local, num_moduli, fastmode=fastmode, dtype=dt, device=dev, backend=backend) if variant == "native" else
              KShardGemm(m, n, k_local, num_moduli, fastmode=fastmode, dtype=dt, device=dev, variant=variant))
         k_tot = k_local * world
         A_full = torch.cat([g8api.randmat(m, k_local, dt, phi=0.5, seed=seedA(r), device=dev) for r in range(world)])
@@ -638,10 +640,10 @@ def verify_against_single_gpu(shard, world, rank, dev, num_moduli, fastmode, var
         n_full, cols = n, slice(rank * nc, (rank + 1) * nc)
     C_loc = torch.zeros(m * nc, dtype=dt, device=dev)
     g.run(A_loc, B_loc, C_loc)
-    tot, _, _ = g8api.work_size(m, n_full, k_tot, num_moduli)
+    tot, _, _ = g8api.work_size(m, n_full, k_tot, num_moduli, backend=backend)
     work = torch.empty(tot, dtype=torch.uint8, device=dev)
     C_full = torch.zeros(m * n_full, dtype=dt, device=dev)
-    g8api.gemm("N", "N", m, n_full, k_tot, 1.0, A_full, m, B_full, k_tot, 0.0, C_full, m, num_moduli, fastmode, work)
+    g8api.gemm("N", "N", m, n_full, k_tot, 1.0, A_full, m, B_full, k_tot, 0.0, C_full, m, num_moduli, fastmode, work, backend=backend)
     torch.cuda.synchronize(dev)
     want = C_full.view(n_full, m)[cols].reshape(-1)
     same = bool(torch.equal(want.view(torch.int64), C_loc.view(torch.int64)))
