@@ -17,7 +17,7 @@ REF_HOOK = ROOT / "oracle" / "_ref" / "libgemmul8_refhook.so"   # the reference'
 
 @pytest.fixture(scope="module")
 def binaries(cuda):
-    if not (NATIVE / "_build" / "sample_kat").exists() or not (NATIVE / "_build" / "hook_check").exists():
+    if not all((NATIVE / "_build" / b).exists() for b in ("sample_kat", "hook_check", "ext_check")):
         subprocess.check_call(["make", "-C", str(NATIVE)])
     return NATIVE / "_build"
 
@@ -26,6 +26,13 @@ def test_cxx_api_sample_known_answer(binaries):
     """sample/dgemm_cuBLAS{,Lt}_int8.cu through gemmul8::gemmLt and gemmul8::gemm: exact product at N=15"""
     r = subprocess.run([str(binaries / "sample_kat")], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "exact" in r.stdout, r.stdout + r.stderr
+
+
+def test_cxx_extension_header_host_and_multi_gpu_front_ends(binaries):
+    """include/gemmul8_ext.hpp (HostGemm, MgComm / MgGemm with a world of one rank) linked against lib/libgemmul8.a: bit-identical to
+    gemmul8::gemmLt for S/D/C/Z, both backends (tests/native/ext_check.cu)"""
+    r = subprocess.run([str(binaries / "ext_check")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ext_check OK" in r.stdout and "MISMATCH" not in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
 def _run_hook(binaries, env_extra, preload):
