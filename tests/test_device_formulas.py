@@ -31,6 +31,8 @@ def test_epilogue_mod_i32(be):
         assert r.min() >= -h and r.max() <= h
         if p % 2:                                   # odd modulus: the unique symmetric representative
             assert np.array_equal(r, ((x + h) % p) - h)
+        else:                                       # even modulus: mulhi under-estimates the quotient, so the tie is always +p/2 --
+            assert np.array_equal(r, h - ((h - x) % p))   # the result is a function of the residue CLASS (range (-p/2, p/2])
 
 
 def test_crt_int8_to_double_splice():
@@ -55,6 +57,23 @@ def test_residue_sum_by_dp4a_selectors():
         pinv = (1 << 32) // p
         r = _sym_wrap(tot - p * ((tot * pinv) >> 32), p)
         assert np.all((r - tot) % p == 0) and np.abs(r).max() <= h
+
+
+def test_fp8_shard_sum_is_canonical():
+    """K-sharded FP8 owner side (i16_sum_parts_kernel): every shard delivers mod_i32 of ITS partial sum; mod_i32 of the sum of those
+    equals mod_i32 of the un-sharded sum for every modulus, ties of the even moduli included -- the owner's C_mid is the single-GPU one."""
+    rng = np.random.default_rng(4)
+
+    def mod_i32(x, p):
+        return _sym_wrap(x - p * ((x * ((1 << 32) // p)) >> 32), p)
+
+    for p in T.moduli("FP8"):
+        h = p // 2
+        parts = rng.integers(-(2 ** 24), 2 ** 24, size=(8, 20000)).astype(np.int64)
+        parts[:, :64] = (np.arange(64) - 32) * h            # multiples of p / 2: the tie cases
+        shard = mod_i32(parts, p)
+        assert np.array_equal(mod_i32(shard.sum(axis=0), p), mod_i32(parts.sum(axis=0), p))
+        assert np.abs(shard.sum(axis=0)).max() < 2 ** 15 * 8
 
 
 def test_fp8_recombination_formulas():
