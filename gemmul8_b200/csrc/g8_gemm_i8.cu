@@ -18,7 +18,7 @@
 // of slots so the epilogue of tile t overlaps the MMAs of tile t+1.  A "unit" is ONE low-precision product: a modulus (real INT8),
 // one of the three 3M products of a modulus (complex INT8) or one FP8 piece product (kind::f8f6f4); multi-product residues are
 // recombined by a small pass in g8_api.cu.  The *_SCATTER epilogues are the fused GEMM -> NVLink exchange of the K-sharded
-// multi-GPU path (residue tiles leave through shared memory + cp.async.bulk into the owning rank's peer-mapped buffer).
+// multi-GPU path (residue tiles leave through swizzled shared memory + one TMA tensor store per warp into the owning rank's peer-mapped buffer).
 #include "g8_internal.cuh"
 
 #include <cuda.h> // CUtensorMap (types only; the encoder is fetched through the runtime, no -lcuda)
@@ -236,8 +236,8 @@ template <> struct EpiCfg<EPI_F8_PROD>        { static constexpr int TILE_COL = 
 // Scatter staging.
 // EPI_MOD_I8_SCATTER: per epilogue warp G8_SCAT_BUFS buffers of 32 columns x 128 rows (4 KB, 128 B per column, 16-byte chunks XOR-swizzled
 // by column & 7 = CU_TENSOR_MAP_SWIZZLE_128B, which also makes the 16-byte shared stores of the 32 lanes conflict-free); ONE TMA tensor
-// store per buffer.  (r02: one 256-byte cp.async.bulk per THREAD -- 256 copy-engine operations per CTA and tile, which cost 10 % of the
-// GEMM even with every receive area on the local GPU; the tensor store needs 8.)
+// store per buffer.  (Before: one 256-byte cp.async.bulk per THREAD, 256 copy-engine operations per CTA and tile against 8 now; measured neutral
+// within noise on 1 and 8 GPUs, profiles/r02i_*.)
 // EPI_RAW_I32_SCATTER (non-default INT32 bound exchange): per thread one 128-byte bulk copy per TMEM chunk from a padded row.
 #ifndef G8_SCAT_BUFS
 #define G8_SCAT_BUFS 2

@@ -40,7 +40,7 @@ enum GemmEpilogue : int {
     EPI_F8_MOD   = 5, // three products per modulus (square moduli: AhBl, AlBh, AlBl; else Karatsuba) -> int16 residue
     EPI_F8_BOUND = 6, // bound product (one plane each), inflated by (k+1)*2^-24, row/col float maxima
     EPI_F8_RAW   = 7, // TEST ONLY: raw f32 accumulator of one product per unit
-    // K-sharded multi-GPU: EPI_MOD_I8 whose residue tiles leave through shared memory + cp.async.bulk (128-byte column segments)
+    // K-sharded multi-GPU: EPI_MOD_I8 whose residue tiles leave through shared memory + one TMA tensor store per warp (32 columns x 128 rows)
     // into the owning rank's peer-mapped buffer.  Selected internally when GemmArgs::owner_cols != 0.
     EPI_MOD_I8_SCATTER = 8,
     EPI_RAW_I32_SCATTER = 9, // same for the raw INT32 partial (the bound product of accurate mode)

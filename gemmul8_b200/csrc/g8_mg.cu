@@ -4,7 +4,7 @@
 // and reconstructs the column slab C[:, n_r].  Everything between the ranks travels over NVLink peer memory (CUDA IPC) through OUR
 // OWN kernels -- no NCCL, no MPI, no Python on this path:
 //   * bulk exchange : the tcgen05 GEMM epilogue scatters its residue tiles straight into the owners' receive areas
-//                     (g8_stage_gemm_scatter: shared memory -> cp.async.bulk -> peer HBM, overlapped with the MMAs of the next tile);
+//                     (g8_stage_gemm_scatter: shared memory -> TMA tensor store -> peer HBM, overlapped with the MMAs of the next tile);
 //   * small vectors : `mg_allreduce_kernel` -- every rank stores its vector into a mailbox slot of every peer, a flag exchange with
 //                     system-scope release / acquire orders the ranks, every rank reduces the slots IN RANK ORDER (so the round-up
 //                     sums of fast mode are identical on every rank, which NCCL does not promise);
