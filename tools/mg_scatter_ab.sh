@@ -1,5 +1,8 @@
 #!/bin/bash
 # 8-GPU A/B of the GEMM -> scatter epilogue: TMA tensor store (default library) vs the previous per-thread bulk copies (variant library)
+# The variant is NOT kept in the tree: build it from the commit before the change with
+#   git show 7adef48:gemmul8_b200/csrc/g8_gemm_i8.cu > /tmp/old.cu   (compile like csrc/Makefile, link the other objects of build/obj)
+# into gemmul8_b200/lib/variants/libg8core_old.so; GEMMUL8_B200_LIB selects the library the Python layer loads.
 N=${1:-8}
 mkdir -p gpurun_out
 run() { # name lib args...
