@@ -104,5 +104,7 @@ def test_argument_validation_needs_no_gpu():
     assert lib.g8_mg_comm_create(ctypes.byref(comm), 9, 0, 4096, handle) == INVALID                       # more than the 8 GPUs of a box
     assert lib.g8_mg_comm_create(ctypes.byref(comm), 2, 2, 4096, handle) == INVALID                       # rank out of range
     assert lib.g8_mg_plan_create(ctypes.byref(plan), None, 1, 0, 0, 256, 256, 256, 14, 0) == INVALID
+    assert lib.g8_mg_plan_create_backend(ctypes.byref(plan), None, 1, 1, 0, 0, 256, 256, 256, 14, 0) == INVALID   # no communicator
+    assert lib.g8_mg_plan_create_backend(ctypes.byref(plan), None, 1, 2, 0, 0, 256, 256, 256, 14, 0) == INVALID   # backend
     assert lib.g8_gemm_mg(None, p, p, 8, p, 8, p, p, 8, None) == INVALID
     assert lib.g8_stage_gemm_bound_chain(p, 256, p, 256, 8, 8, 256, 0, p, p, None) != 0                   # chain < 1 (or no device)
