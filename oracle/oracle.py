@@ -175,16 +175,25 @@ def accurate_shifts_fp8(A: Operand, B: Operand, num_moduli: int):
     log2P = np.float32(T.log2P("FP8", num_moduli))
     k = A.inner
 
+    cplx = np.iscomplexobj(A.view)
+
     def s0_and_bar(O):
-        v = O.view.astype(np.float64)
-        amax = np.abs(v).max(axis=1) if O.inner else np.zeros(O.rows)
+        parts = [np.asarray(pz, dtype=np.float64) for pz in _real_parts(O.view)]
+        amax = np.zeros(O.rows)
+        for pz in parts:
+            amax = np.maximum(amax, np.abs(pz).max(axis=1) if O.inner else 0.0)
         s0 = np.array([7 - ilogb_exact(float(a)) for a in amax], dtype=np.int16)
-        bar = e4m3_round_up(np.abs(v) * np.exp2(s0.astype(np.float64))[:, None])
-        return s0, bar
+        return s0, [e4m3_round_up(np.abs(pz) * np.exp2(s0.astype(np.float64))[:, None]) for pz in parts]
 
     s0A, Abar = s0_and_bar(A)
     s0B, Bbar = s0_and_bar(B)
-    Cbar = Abar @ Bbar.T  # exact enough in f64 (values < 2^8, k <= 2^16)
+    if not cplx:
+        Cbar = Abar[0] @ Bbar[0].T  # exact enough in f64 (values < 2^8, k <= 2^16)
+    else:
+        # complex: |Re| and |Im| of the product are bounded by |Ar||Br| + |Ai||Bi| and |Ar||Bi| + |Ai||Br| (2k-term sums on the device)
+        (ar, ai), (br, bi) = Abar, Bbar
+        Cbar = np.maximum(ar @ br.T + ai @ bi.T, ar @ bi.T + ai @ br.T)
+        k = 2 * k
     ku = (k + 1) * 2.0 ** -24
 
     def fin(s0, mx):

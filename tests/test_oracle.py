@@ -158,3 +158,38 @@ def test_oracle_fp8_backend_accuracy(dtype, N):
     ref = A.astype(wide) @ B.astype(wide)
     err = np.abs(r["C"] - ref).max() / np.abs(ref).max()
     assert err < 64 * np.finfo(np.dtype(dtype)).eps, err
+
+
+def _mod_i32(x, p):
+    """csrc/g8_common.cuh:mod_i32 replayed on int64 arrays (see tests/test_device_formulas.py)"""
+    r = x - p * ((x * ((1 << 32) // p)) >> 32)
+    h = p >> 1
+    r = np.where(r > h, r - p, r)
+    return np.where(r < -h, r + p, r)
+
+
+@pytest.mark.parametrize("dtype,backend,N", [(np.float64, "INT8", 9), (np.float64, "FP8", 8), (np.complex128, "FP8", 7), (np.complex64, "INT8", 5)])
+def test_k_sharded_residues_sum_to_the_unsharded_ones(dtype, backend, N):
+    """The algebra behind the K-sharded multi-GPU paths (csrc/g8_mg.cu), at the oracle level: with the GLOBAL shifts, every shard's
+    C_mid (the residues of its partial product) summed over the shards and reduced again with the device's mod_i32 equals the C_mid of
+    the un-sharded call bit for bit -- INT8 (crt_parts / i8_cplx_combine_parts) and FP8 (i16_sum_parts), real and complex."""
+    rng = np.random.default_rng(77)
+    m, n, kl, W = 24, 20, 40, 3
+    cplx = np.dtype(dtype).kind == "c"
+    def rand(shape):
+        x = rng.standard_normal(shape) * np.exp(rng.standard_normal(shape))
+        return (x + 1j * rng.standard_normal(shape)).astype(dtype) if cplx else x.astype(dtype)
+    A, B = rand((m, kl * W)), rand((kl * W, n))
+    full = O.emulate(A, B, num_moduli=N, fastmode=False, backend=backend)
+    tot = None
+    for s in range(W):
+        ks = slice(s * kl, (s + 1) * kl)
+        part = O.emulate(A[:, ks], B[ks, :], num_moduli=N, fastmode=False, backend=backend, sftA=full["sftA"], sftB=full["sftB"])
+        tot = part["C_mid"].astype(np.int64) if tot is None else tot + part["C_mid"].astype(np.int64)
+    mods = T.moduli(backend)[:N]
+    for i, p in enumerate(mods):
+        got = _mod_i32(tot[i], p)
+        want = full["C_mid"][i].astype(np.int64)
+        if backend == "INT8" and p == 256:
+            got = got.astype(np.int8).astype(np.int64)     # +128 wraps in the int8 store, as in the reference
+        assert np.array_equal(got, want), f"modulus {p}"
