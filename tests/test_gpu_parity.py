@@ -81,6 +81,28 @@ def test_edge_shapes(env, shape):
             _oracle_check(env, A, B, "N", "N", N, fast)
 
 
+def test_empty_dimensions(env):
+    """BLAS quick-return semantics: k = 0 leaves C = beta * C (the product is empty), m = 0 or n = 0 touches nothing; status 0."""
+    torch = env.torch
+    import gemmul8_b200 as g8
+
+    m, n = 70, 50
+    dummy = torch.ones(64, dtype=torch.float64, device="cuda")
+    C0 = torch.randn(m * n, dtype=torch.float64, device="cuda")
+    work = torch.empty(16 << 20, dtype=torch.uint8, device="cuda")
+    for fast in (False, True):
+        for beta in (0.0, 0.5):
+            C = C0.clone()
+            g8.gemm("N", "N", m, n, 0, 1.0, dummy, m, dummy, 1, beta, C, m, 14, fast, work)
+            torch.cuda.synchronize()
+            assert torch.equal(C, beta * C0), (fast, beta)
+        for mm, nn in ((0, n), (m, 0)):
+            C = C0.clone()
+            g8.gemm("N", "N", mm, nn, 33, 1.0, dummy, max(mm, 1), dummy, 33, 0.0, C, max(mm, 1), 14, fast, work)
+            torch.cuda.synchronize()
+            assert torch.equal(C, C0), (fast, mm, nn)
+
+
 @pytest.mark.parametrize("alpha,beta,dev", [(1, 1, False), (-1, 0, False), (-1, 1, False), (0.75, -1.5, False), (0.75, -1.5, True), (1, 0, True), (0, 1, False)])
 def test_alpha_beta_and_leading_dimensions(env, alpha, beta, dev):
     """the five (alpha,beta) classes of debug/test.cu:106-141, host and device scalars, lda/ldb/ldc > rows"""
